@@ -1,0 +1,45 @@
+// Internal launcher interface between the C ABI (b200mel_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "logmel_core.cuh"
+#include "tables.h"
+
+namespace b200mel {
+
+struct LogmelArgs {
+    const void* audio;       // device, [batch, n_samples] rows, pitch stride_b elements
+    int64_t stride_b;
+    int64_t n_samples;       // samples per row present in memory
+    int64_t total;           // n_samples + right zero pad: the length torch.stft sees
+    const int32_t* lengths;  // device int32 [batch] or nullptr
+    int64_t batch;           // utterances in this launch
+    int n_frames;            // T = total / 160
+    int n_mels;
+    float* out;              // device, [batch, n_mels, T]
+    uint32_t* max_keys;      // device, [batch] (or [1] with global_max), order-preserving keys
+    int global_max;
+    const DeviceTables* tables;  // device
+};
+
+// FFT variant, pass 1: un-normalised log10 mel + per-utterance max keys.
+cudaError_t launch_fft_pass1(const LogmelArgs& a, int dtype, cudaStream_t stream);
+// Pass 2 (shared by all variants): out = (max(out, g - 8) + 4) / 4.
+cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip,
+                             int global_max, cudaStream_t stream);
+
+uint64_t launches_so_far();
+void count_launch(unsigned n = 1);
+
+// Optional event bracketing of a launch (b200mel_profile_enable); kind indexes B200MEL_PROFILE_KINDS.
+struct ProfileScope {
+    ProfileScope(int kind, cudaStream_t stream);
+    ~ProfileScope();
+    cudaEvent_t start_ = nullptr, stop_ = nullptr;
+    cudaStream_t stream_ = nullptr;
+    int kind_ = 0;
+};
+
+}  // namespace b200mel

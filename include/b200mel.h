@@ -1,0 +1,128 @@
+/* b200mel — C ABI of the B200-native fused log-mel front-end.
+ *
+ * This is the drop-in boundary for the hot path of muhkemallgp/asr-ttl-mtl,
+ * `whisper/audio.py` (reference file:line cited per entry point).  The reference
+ * has no FFI of its own (pure Python calling torch operators); the module
+ * namespace of whisper/audio.py is its operator API, so these entry points are
+ * what a Python binding for that module needs: plain pointers, sizes and a
+ * CUDA stream handle — no torch types.  The ctypes stub that binds them lives
+ * in asr-ttl-mtl_b200/_native.py and is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns a b200mel_status (0 = ok); nothing throws.
+ *   - device pointers are raw CUDA device addresses on the CURRENT device;
+ *     ownership stays with the caller (torch allocates; see audio.py mirror).
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no host
+ *     synchronisation happens inside the *_device entry points.
+ *   - thread-safe: plans are immutable after creation; calls on different
+ *     streams may run concurrently as long as they use different workspaces.
+ */
+#ifndef B200MEL_H_
+#define B200MEL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MEL_ABI_VERSION 1
+
+/* audio constants of whisper/audio.py:13-22 */
+#define B200MEL_SAMPLE_RATE 16000
+#define B200MEL_N_FFT 400
+#define B200MEL_HOP_LENGTH 160
+#define B200MEL_N_BINS 201
+
+typedef enum b200mel_status {
+    B200MEL_OK = 0,
+    B200MEL_ERR_NULL_POINTER = 1,
+    B200MEL_ERR_BAD_N_MELS = 2,   /* audio.py:103  assert n_mels in {80, 128}            */
+    B200MEL_ERR_TOO_SHORT = 3,    /* torch.stft reflect pad needs n_samples + pad > 200  */
+    B200MEL_ERR_BAD_ARGUMENT = 4, /* negative sizes, unknown dtype / variant, ...        */
+    B200MEL_ERR_BAD_FILTERS = 5,  /* filterbank rows are not single contiguous bands     */
+    B200MEL_ERR_CUDA = 6,         /* a CUDA runtime call or launch failed (see last_cuda_error) */
+    B200MEL_ERR_NO_DEVICE = 7     /* no sm_100 device visible: there is NO CPU fallback  */
+} b200mel_status;
+
+typedef enum b200mel_dtype {
+    B200MEL_F32 = 0, /* float32 waveform in [-1, 1]                       (audio.py:141) */
+    B200MEL_S16 = 1  /* int16 PCM; scaled by 1/32768 in-register          (audio.py:62)  */
+} b200mel_dtype;
+
+typedef enum b200mel_variant {
+    B200MEL_VARIANT_AUTO = 0,   /* the variant ncu picked                 */
+    B200MEL_VARIANT_FFT = 1,    /* shared-memory mixed-radix (20x20) real FFT, fp32 CUDA cores */
+    B200MEL_VARIANT_TCGEN05 = 2 /* DFT-as-GEMM on tcgen05 tensor cores, 3xTF32 compensation    */
+} b200mel_variant;
+
+/* flags for b200mel_logmel_device / _host */
+#define B200MEL_FLAG_GLOBAL_MAX 1u /* one max over the whole call: the reference's literal
+                                      behaviour for a 2-D input (audio.py:155).  Default is one
+                                      max per utterance (stack of per-clip calls).             */
+
+typedef struct b200mel_plan b200mel_plan; /* opaque: filterbank bands + FFT tables on one device */
+
+int b200mel_abi_version(void);
+const char* b200mel_status_string(int status);
+/* text of the last CUDA error seen by this thread (empty string if none) */
+const char* b200mel_last_cuda_error(void);
+
+/* Frame count rule of audio.py:145-149: T = (n_samples + max(right_zero_pad, 0)) / 160,
+ * B200MEL_ERR_TOO_SHORT if n_samples + pad <= 200. */
+int b200mel_frames(int64_t n_samples, int64_t right_zero_pad, int64_t* n_frames);
+
+/* Replaces mel_filters(device, n_mels) + torch.hann_window (audio.py:91-107, :147) as the
+ * kernel's constant operands.  filters_host: float32 [n_mels, 201] row-major in HOST memory.
+ * The plan lives on the current CUDA device. */
+int b200mel_plan_create(int n_mels, const float* filters_host, b200mel_plan** plan_out);
+int b200mel_plan_destroy(b200mel_plan* plan);
+int b200mel_plan_n_mels(const b200mel_plan* plan);
+
+/* Bytes of device scratch b200mel_logmel_device needs for `batch` utterances. */
+size_t b200mel_workspace_bytes(int64_t batch);
+
+/* Replaces log_mel_spectrogram's compute, audio.py:145-156, for a batch of utterances.
+ *   audio      device, [batch, n_samples] of `dtype`, row pitch `stride_b` ELEMENTS
+ *   lengths    device int32 [batch] or NULL: samples of each row that are real; the rest of the
+ *              row is treated as zeros WITHOUT being read (pad_or_trim semantics, audio.py:83-86)
+ *   right_zero_pad  the `padding` argument (audio.py:145-146); <= 0 is ignored
+ *   out        device float32 [batch, n_mels, T] contiguous, T from b200mel_frames
+ *   workspace  device scratch of b200mel_workspace_bytes(batch)
+ *   l2_chunk_clips  utterances per L2-resident pass (0 = library default)
+ */
+int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype, int64_t batch,
+                          int64_t n_samples, int64_t stride_b, const int32_t* lengths,
+                          int64_t right_zero_pad, float* out, void* workspace, unsigned flags,
+                          int variant, int l2_chunk_clips, void* stream);
+
+/* Second pass only: out = (max(out, g - 8) + 4) / 4 with g decoded from `workspace`
+ * (audio.py:155-156).  Exposed for tests; b200mel_logmel_device already runs it. */
+int b200mel_normalise_device(float* out, const void* workspace, int64_t batch, int64_t elems_per_clip,
+                             unsigned flags, void* stream);
+
+/* Host-buffer entry point (what a CPU-tensor caller of log_mel_spectrogram hits, audio.py:138-144):
+ * audio_host / out_host are HOST pointers (pinned for full speed).  Copies in, computes and copies
+ * out in chunks on internal streams so H2D, compute and D2H overlap; returns after the result
+ * is complete in out_host. */
+int b200mel_logmel_host(const b200mel_plan* plan, const void* audio_host, int dtype, int64_t batch,
+                        int64_t n_samples, int64_t stride_b, const int32_t* lengths_host,
+                        int64_t right_zero_pad, float* out_host, unsigned flags, int variant);
+
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t b200mel_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline: while enabled, every kernel launch is
+ * bracketed by CUDA events on its own stream.  b200mel_profile_collect synchronises those
+ * events, adds their durations per kernel kind and clears the list.
+ *   kinds: 0 = FFT-variant fused pass, 1 = normalise pass, 2 = tcgen05-variant fused pass, 3 = other
+ *   ms_by_kind / launches_by_kind: arrays of B200MEL_PROFILE_KINDS entries */
+#define B200MEL_PROFILE_KINDS 4
+int b200mel_profile_enable(int on);
+int b200mel_profile_collect(double* ms_by_kind, uint64_t* launches_by_kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MEL_H_ */

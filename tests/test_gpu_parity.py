@@ -1,0 +1,238 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors and the oracle.  `-m gpu`.
+
+Bar: bit-exact shapes / frame counts / pad-trim indexing; <= 1e-4 max-abs on
+the normalised log-mel in fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel_oracle as orc
+from oracle import signals
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+VARIANTS = ["fft"]
+
+
+def _maxerr(a, b):
+    return float((torch.as_tensor(a).double().cpu() - torch.as_tensor(b).double().cpu()).abs().max())
+
+
+def test_library_is_the_thing_that_runs(b200):
+    before = b200.gpu_launches()
+    b200.log_mel_spectrogram(torch.zeros(16000, device=DEV))
+    torch.cuda.synchronize()
+    assert b200.gpu_launches() >= before + 2  # fused pass + normalise pass
+
+
+def test_golden_cases_single_utterance_api(b200, golden):
+    worst = 0.0
+    for c in golden.cases:
+        x = golden.signal(c)
+        got = b200.log_mel_spectrogram(x, n_mels=c["n_mels"], padding=c["padding"], device=DEV)
+        assert got.device.type == "cuda" and got.dtype == torch.float32 and got.is_contiguous()
+        assert tuple(got.shape) == tuple(c["shape"])
+        err = _maxerr(got, golden.out(c))
+        worst = max(worst, err)
+        assert err <= TOL, (c, err)
+    print(f"worst golden error {worst:.3e}")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_batch_is_per_utterance_stack_of_oracle_calls(b200, n_mels, variant):
+    kinds = list(signals.KINDS)
+    batch = np.stack([signals.make_signal(k, 40000, 300 + i) for i, k in enumerate(kinds)])
+    got = b200.log_mel_spectrogram_batch(torch.from_numpy(batch).to(DEV), n_mels=n_mels, variant=variant)
+    want = orc.logmel_f32_port_per_utterance(torch.from_numpy(batch), n_mels)
+    assert tuple(got.shape) == (len(kinds), n_mels, 250)
+    for i, k in enumerate(kinds):
+        assert _maxerr(got[i], want[i]) <= TOL, (k, _maxerr(got[i], want[i]))
+    f64 = np.stack([orc.logmel_f64(x, n_mels) for x in batch])
+    # adversarial signals: stay as close to the float64 spec as the reference does (+5e-5)
+    for i, k in enumerate(kinds):
+        assert _maxerr(got[i], f64[i]) <= _maxerr(want[i], f64[i]) + 5e-5, k
+
+
+def test_reference_2d_semantics_one_max_per_call(b200, golden):
+    scale = golden["batch2d_in_scale"]
+    batch = np.stack([signals.make_signal("gauss", 16000, 50) * s for s in scale])
+    got = b200.log_mel_spectrogram(torch.from_numpy(batch), device=DEV)  # drop-in API: global max
+    assert _maxerr(got, golden["batch2d_out"]) <= TOL
+    per = b200.log_mel_spectrogram_batch(torch.from_numpy(batch).to(DEV))
+    assert _maxerr(per, golden["batch2d_out"]) > 0.1
+
+
+def test_lengths_fast_path_equals_zero_filled_rows(b200):
+    lens = np.array([0, 1, 201, 16000, 31999, 47999, 48000, 52000], dtype=np.int64)
+    rows = np.stack([signals.make_signal("gauss", 48000, 900 + i) for i in range(len(lens))])
+    padded = rows.copy()
+    for i, n in enumerate(lens):
+        padded[i, min(n, 48000):] = 0.0
+    a = b200.log_mel_spectrogram_batch(torch.from_numpy(rows).to(DEV), lengths=torch.from_numpy(lens))
+    b = b200.log_mel_spectrogram_batch(torch.from_numpy(padded).to(DEV))
+    assert torch.equal(a, b)  # same arithmetic on the same values
+    want = orc.logmel_f32_port_per_utterance(torch.from_numpy(padded), 80)
+    assert _maxerr(a, want) <= TOL
+    assert torch.all(a[0] == -1.5)  # an all-zero utterance (reference: every value (-10+4)/4)
+
+
+def test_variable_length_clips_like_the_training_set(b200):
+    # BASELINE config 4: 1-30 s clips pad_or_trim-med to N_SAMPLES, batches of 16
+    lens = signals.variable_lengths(16)
+    clips = [signals.make_signal("gauss", int(n), 40 + i) for i, n in enumerate(lens)]
+    padded = np.stack([b200.pad_or_trim(c) for c in clips])
+    assert padded.shape == (16, 480000)
+    got = b200.log_mel_spectrogram_batch(torch.from_numpy(padded).to(DEV), lengths=torch.from_numpy(lens))
+    assert tuple(got.shape) == (16, 80, 3000)
+    for i in (0, 5, 15):
+        want = orc.logmel_f32_port(padded[i], 80)
+        assert _maxerr(got[i], want) <= TOL
+        tail = got[i][:, int(lens[i]) // 160 + 3:]
+        if tail.numel():
+            assert torch.all(tail == tail.flatten()[0])  # silence sits exactly on the max-8 clamp
+            assert abs(float(got[i].max() - tail.flatten()[0]) - 2.0) < 1e-6
+
+
+def test_pcm16_ingest_is_bit_equal_to_the_float_path(b200):
+    q = np.stack([signals.make_pcm16(32000, 60 + i) for i in range(4)])
+    f = q.astype(np.float32) / 32768.0  # audio.py:62
+    a = b200.log_mel_spectrogram_batch(torch.from_numpy(q).to(DEV), n_mels=128)
+    b = b200.log_mel_spectrogram_batch(torch.from_numpy(f).to(DEV), n_mels=128)
+    assert torch.equal(a, b)
+    assert _maxerr(a, orc.logmel_f32_port_per_utterance(torch.from_numpy(f), 128)) <= TOL
+
+
+def test_host_buffer_entry_point_matches_device_path(b200):
+    x = np.stack([signals.make_signal("uniform", 480000, 70 + i) for i in range(5)])
+    dev = b200.log_mel_spectrogram_batch(torch.from_numpy(x).to(DEV)).cpu()
+    host = b200.log_mel_spectrogram_batch(torch.from_numpy(x))  # CPU tensor in -> CPU tensor out
+    assert host.device.type == "cpu" and torch.equal(host, dev)
+    pinned = torch.from_numpy(x).pin_memory()
+    out = torch.empty(5, 80, 3000).pin_memory()
+    res = b200.log_mel_spectrogram_batch(pinned, out=out)
+    assert res.data_ptr() == out.data_ptr() and torch.equal(out, dev)
+    single = b200.log_mel_spectrogram(x[2])  # numpy in, like dataset.py:89
+    assert single.device.type == "cpu" and torch.equal(single, dev[2])
+    lens = torch.tensor([480000, 1000, 240000, 0, 479999])
+    a = b200.log_mel_spectrogram_batch(torch.from_numpy(x), lengths=lens)
+    b = b200.log_mel_spectrogram_batch(torch.from_numpy(x).to(DEV), lengths=lens).cpu()
+    assert torch.equal(a, b)
+
+
+def test_non_contiguous_and_strided_rows(b200):
+    base = torch.from_numpy(np.stack([signals.make_signal("gauss", 20000, 80 + i) for i in range(6)])).to(DEV)
+    rows = base[::2]  # row pitch 2 * L, inner stride 1: consumed in place through stride_b
+    assert torch.equal(b200.log_mel_spectrogram_batch(rows), b200.log_mel_spectrogram_batch(rows.contiguous()))
+    inter = base.t().contiguous().t()  # inner stride != 1 -> copied by the wrapper
+    assert torch.equal(b200.log_mel_spectrogram_batch(inter), b200.log_mel_spectrogram_batch(base))
+    odd = base[:, 1:]  # 4-byte aligned rows (no 16-byte alignment)
+    want = orc.logmel_f32_port_per_utterance(odd.cpu(), 80)
+    assert _maxerr(b200.log_mel_spectrogram_batch(odd), want) <= TOL
+
+
+def test_transcribe_call_pattern(b200):
+    # transcribe.py:139-141: whole file, padding=N_SAMPLES, then pad_or_trim(mel, N_FRAMES) windows
+    x = signals.make_signal("sine1k_noise", 16000 * 47 + 123, 9)
+    mel = b200.log_mel_spectrogram(x, 80, padding=b200.N_SAMPLES, device=DEV)
+    assert tuple(mel.shape) == (80, (x.size + 480000) // 160)
+    assert _maxerr(mel, orc.logmel_f32_port(x, 80, padding=480000)) <= TOL
+    content_frames = mel.shape[-1] - b200.N_FRAMES
+    seg = b200.pad_or_trim(mel[:, 3000:3000 + min(3000, content_frames - 3000)], b200.N_FRAMES)
+    assert tuple(seg.shape) == (80, 3000) and seg.device.type == "cuda"
+
+
+def test_nan_and_inf_poison_only_their_own_utterance(b200):
+    x = np.stack([signals.make_signal("gauss", 16000, 20 + i) for i in range(3)])
+    x[1, 777] = np.nan
+    x[2, 12345] = np.inf
+    got = b200.log_mel_spectrogram_batch(torch.from_numpy(x).to(DEV)).cpu()
+    assert not torch.isnan(got[0]).any()
+    assert torch.isnan(got[1]).all() and torch.isnan(got[2]).all()  # torch.max propagates NaN (audio.py:155)
+    assert torch.isnan(orc.logmel_f32_port(x[1], 80)).all()
+
+
+def test_error_behaviour_matches_the_reference(b200):
+    with pytest.raises(AssertionError, match="Unsupported n_mels"):
+        b200.log_mel_spectrogram(torch.zeros(16000, device=DEV), n_mels=100)
+    with pytest.raises(RuntimeError):
+        b200.log_mel_spectrogram(torch.zeros(200, device=DEV))  # reflect pad needs > 200 samples
+    with pytest.raises(RuntimeError):
+        b200.log_mel_spectrogram(torch.zeros(2, 3, 1600, device=DEV))
+    with pytest.raises(RuntimeError):
+        b200.log_mel_spectrogram(torch.zeros(16000, device=DEV, dtype=torch.float64))
+    assert tuple(b200.log_mel_spectrogram(torch.zeros(201, device=DEV)).shape) == (80, 1)
+    assert tuple(b200.log_mel_spectrogram(torch.zeros(100, device=DEV), padding=101).shape) == (80, 1)
+    assert tuple(b200.log_mel_spectrogram(torch.zeros(1000, device=DEV), padding=-7).shape) == (80, 6)
+
+
+def test_input_is_not_aliased_or_modified(b200):
+    x = torch.from_numpy(signals.make_signal("gauss", 16000, 1)).to(DEV)
+    keep = x.clone()
+    out = b200.log_mel_spectrogram(x)
+    assert torch.equal(x, keep) and out.data_ptr() != x.data_ptr() and not out.requires_grad
+
+
+def test_runs_on_the_current_stream(b200):
+    x = torch.from_numpy(signals.make_signal("gauss", 48000, 2)).to(DEV)
+    ref = b200.log_mel_spectrogram(x)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        y = b200.log_mel_spectrogram(x)
+    side.synchronize()
+    assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_full_size_batch_properties(b200, n_mels):
+    # BASELINE configs 2 / 3 at full size: 256 clips x 30 s, checked through size-independent properties
+    gen = torch.Generator(device=DEV).manual_seed(1234)
+    audio = (0.1 * torch.randn(256, 480000, generator=gen, device=DEV)).clamp_(-1, 1)
+    audio[17] = audio[3]            # replicas of one clip at different batch positions
+    audio[200] = audio[3]
+    out = b200.log_mel_spectrogram_batch(audio, n_mels=n_mels)
+    assert tuple(out.shape) == (256, n_mels, 3000)
+    assert torch.equal(out[17], out[3]) and torch.equal(out[200], out[3])
+    # chunking is invisible: any L2 chunk size gives the same bytes
+    assert torch.equal(b200.log_mel_spectrogram_batch(audio, n_mels=n_mels, l2_chunk_clips=7), out)
+    # dynamic range: every utterance spans at most 8 decades => (max - min) <= 2 after (x+4)/4
+    mx, mn = out.amax(dim=(1, 2)), out.amin(dim=(1, 2))
+    assert torch.all(mx - mn <= 2.0 + 1e-6) and torch.isfinite(out).all()
+    # idempotence of the call and independence from the rest of the batch
+    assert torch.equal(b200.log_mel_spectrogram_batch(audio[3:4], n_mels=n_mels)[0], out[3])
+    # spot-check three clips against the oracle
+    for i in (0, 3, 255):
+        assert _maxerr(out[i], orc.logmel_f32_port(audio[i].cpu(), n_mels)) <= TOL
+    # checksum of checksums is reproducible run to run
+    again = b200.log_mel_spectrogram_batch(audio, n_mels=n_mels)
+    assert float(out.double().sum(dim=(1, 2)).sum()) == float(again.double().sum(dim=(1, 2)).sum())
+
+
+def test_long_single_utterance(b200):
+    # one hour-scale file in one call (transcribe path): one max over the whole file
+    x = signals.make_signal("gauss", 16000 * 600, 3)  # 10 minutes
+    x[: 16000 * 5] *= 1e-3
+    got = b200.log_mel_spectrogram(x, device=DEV)
+    want = orc.logmel_f32_port(x, 80)
+    assert tuple(got.shape) == (80, 60000) and _maxerr(got, want) <= TOL
+
+
+def test_normalise_entry_point(b200, native_lib):
+    from asr_ttl_mtl_b200 import _native
+
+    vals = torch.tensor([[-10.0, -3.0, 0.5, 1.0], [2.0, -9.0, -5.9, -6.1]], device=DEV)
+    keys = torch.zeros(64, dtype=torch.int32, device=DEV)
+    enc = []
+    for row in vals.cpu():
+        bits = np.float32(row.max().item()).view(np.uint32)
+        enc.append(int(bits | 0x80000000) if not (bits & 0x80000000) else int(~bits & 0xFFFFFFFF))
+    keys[:2] = torch.tensor(np.array(enc, dtype=np.uint32).view(np.int32))
+    out = vals.clone()
+    _native.check(native_lib.b200mel_normalise_device(out.data_ptr(), keys.data_ptr(), 2, 4, 0,
+                                                      torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    want = (torch.maximum(vals, vals.amax(dim=1, keepdim=True) - 8.0) + 4.0) / 4.0
+    assert torch.equal(out, want)
