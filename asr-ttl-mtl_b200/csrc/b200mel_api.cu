@@ -66,6 +66,7 @@ constexpr int kHostSlots = 3;
 struct b200mel_plan {
     int device = -1;
     int n_mels = 0;
+    int n_rows = 0;  // rows of the mel partial-sum tile (DeviceTables::n_rows)
     b200mel::DeviceTables* d_tables = nullptr;
     std::mutex host_mutex;  // the host pipeline's staging buffers are per plan
     b200mel::HostSlot slots[b200mel::kHostSlots];
@@ -75,15 +76,9 @@ namespace b200mel {
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int default_chunk_clips(int n_mels, int64_t n_frames) {
-    // keep one chunk's un-normalised output (written by pass 1, re-read by pass 2) well inside
-    // the 126 MB L2 next to the streaming input: ~32 MB of output per chunk
-    const int64_t bytes_per_clip = static_cast<int64_t>(n_mels) * n_frames * 4;
-    int64_t c = (32ll << 20) / (bytes_per_clip > 0 ? bytes_per_clip : 1);
-    if (c < 1) c = 1;
-    if (c > 4096) c = 4096;
-    return static_cast<int>(c);
-}
+// An utterance longer than this many 32-frame tiles (~5 min of audio) is normalised by the
+// stand-alone pass-2 kernel instead of by the single CTA that finishes it.
+constexpr int64_t kMaxFusedNormTiles = 1024;
 
 static void free_slot(HostSlot& s) {
     if (s.d_in) cudaFree(s.d_in);
@@ -183,6 +178,7 @@ int b200mel_plan_create(int n_mels, const float* filters_host, b200mel_plan** pl
     b200mel_plan* plan = new (std::nothrow) b200mel_plan();
     if (plan == nullptr) return B200MEL_ERR_BAD_ARGUMENT;
     plan->n_mels = n_mels;
+    plan->n_rows = host[0].n_rows;
     cudaError_t e = cudaGetDevice(&plan->device);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&plan->d_tables), sizeof(DeviceTables));
     if (e == cudaSuccess) e = cudaMemcpy(plan->d_tables, host.data(), sizeof(DeviceTables), cudaMemcpyHostToDevice);
@@ -205,9 +201,10 @@ int b200mel_plan_destroy(b200mel_plan* plan) {
 
 int b200mel_plan_n_mels(const b200mel_plan* plan) { return plan ? plan->n_mels : 0; }
 
+// workspace = [max keys: batch u32][completion counters: batch u32][tile queue head: 1 u32]
 size_t b200mel_workspace_bytes(int64_t batch) {
     if (batch < 1) batch = 1;
-    return round_up(static_cast<size_t>(batch) * sizeof(uint32_t), 256);
+    return round_up((2 * static_cast<size_t>(batch) + 1) * sizeof(uint32_t), 256);
 }
 
 int b200mel_normalise_device(float* out, const void* workspace, int64_t batch, int64_t elems_per_clip,
@@ -239,32 +236,31 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int global_max = (flags & B200MEL_FLAG_GLOBAL_MAX) ? 1 : 0;
     uint32_t* keys = static_cast<uint32_t*>(workspace);
-    B200_CUDA(cudaMemsetAsync(keys, 0, sizeof(uint32_t) * (global_max ? 1 : batch), stream));
+    B200_CUDA(cudaMemsetAsync(keys, 0, (2 * static_cast<size_t>(batch) + 1) * sizeof(uint32_t), stream));
 
     const int64_t elems_per_clip = static_cast<int64_t>(plan->n_mels) * n_frames;
-    const size_t in_elem = dtype == B200MEL_F32 ? sizeof(float) : sizeof(int16_t);
-    const int64_t chunk = l2_chunk_clips > 0 ? l2_chunk_clips : default_chunk_clips(plan->n_mels, n_frames);
+    const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
+    (void)l2_chunk_clips;  // the persistent kernel walks the batch clip-major; nothing to chunk
 
     LogmelArgs a;
+    a.audio = audio;
     a.stride_b = stride_b;
     a.n_samples = n_samples;
     a.total = n_samples + (right_zero_pad > 0 ? right_zero_pad : 0);
+    a.lengths = lengths;
+    a.batch = batch;
     a.n_frames = static_cast<int>(n_frames);
     a.n_mels = plan->n_mels;
+    a.out = out;
+    a.max_keys = keys;
+    a.done_counters = keys + batch;
+    a.tile_counter = keys + 2 * batch;
     a.global_max = global_max;
+    a.fused_norm = (!global_max && tiles_per_clip <= kMaxFusedNormTiles) ? 1 : 0;
+    a.n_rows = plan->n_rows;
     a.tables = plan->d_tables;
-    for (int64_t c0 = 0; c0 < batch; c0 += chunk) {
-        const int64_t n = (batch - c0 < chunk) ? batch - c0 : chunk;
-        a.audio = static_cast<const char*>(audio) + static_cast<size_t>(c0) * stride_b * in_elem;
-        a.lengths = lengths ? lengths + c0 : nullptr;
-        a.batch = n;
-        a.out = out + c0 * elems_per_clip;
-        a.max_keys = global_max ? keys : keys + c0;
-        B200_CUDA(launch_fft_pass1(a, dtype, stream));
-        if (!global_max)
-            B200_CUDA(launch_normalise(a.out, a.max_keys, n, elems_per_clip, 0, stream));
-    }
-    if (global_max) B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, 1, stream));
+    B200_CUDA(launch_fft_fused(a, dtype, stream));
+    if (!a.fused_norm) B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, global_max, stream));
     return B200MEL_OK;
 }
 

@@ -20,12 +20,17 @@ struct LogmelArgs {
     int n_mels;
     float* out;              // device, [batch, n_mels, T]
     uint32_t* max_keys;      // device, [batch] (or [1] with global_max), order-preserving keys
+    uint32_t* done_counters; // device, [batch]: warps that finished a tile of the utterance (fused normalise)
+    uint32_t* tile_counter;  // device, [1]: the persistent kernel's tile queue head
     int global_max;
+    int fused_norm;          // the last CTA to finish an utterance normalises it in place
+    int n_rows;              // rows of the mel partial-sum tile (DeviceTables::n_rows)
     const DeviceTables* tables;  // device
 };
 
-// FFT variant, pass 1: un-normalised log10 mel + per-utterance max keys.
-cudaError_t launch_fft_pass1(const LogmelArgs& a, int dtype, cudaStream_t stream);
+// FFT variant, one persistent launch: log10 mel + per-utterance max keys (+ in-place normalise when
+// a.fused_norm).  The counters in `a` must be zero when the kernel starts.
+cudaError_t launch_fft_fused(const LogmelArgs& a, int dtype, cudaStream_t stream);
 // Pass 2 (shared by all variants): out = (max(out, g - 8) + 4) / 4.
 cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip,
                              int global_max, cudaStream_t stream);

@@ -43,6 +43,18 @@ constexpr int kGroupStride = kRadix * kYStride;       // 420 float2 of scratch p
 constexpr int kOutStride = kTileFrames + 1;           // padded row of the output staging tile
 constexpr int kMaxMelWeights = 512;                   // packed non-zero filter weights (<= 394 used)
 constexpr int kMaxMels = 128;
+constexpr int kPStride = 34;                          // padded row of the power tile P[bin][frame]
+constexpr int kSegBins = 20;                          // bins swept by one warp (10 warps x 20 = 200 bins)
+constexpr int kSegments = kUsedBins / kSegBins;       // == warps per CTA
+constexpr int kSStride = kTileFrames + 1;             // padded row of the partial-sum tile S[row][frame]
+constexpr int kMaxSRows = kMaxMels + 32;              // mel rows + second parts of segment-straddling mels
+constexpr int kWarpsPerCta = kThreads / 32;
+static_assert(kSegments == kWarpsPerCta, "one 20-bin segment per warp");
+
+// One bin of the warp-uniform mel sweep.  w0/w1: weight of the active even/odd mel at this
+// bin (0 if none).  emit: low/high 16 bits = S row that receives slot 0/1 after this bin,
+// 0xffff = keep accumulating.
+struct MelSweepEntry { float w0, w1; unsigned emit; int pad; };
 
 // Packed per-mel band descriptor: first bin | count << 8 | weight offset << 16.
 B200_HD int mel_band_pack(int first, int count, int offset) { return first | (count << 8) | (offset << 16); }
@@ -156,23 +168,26 @@ B200_HD float normalise(float lg, float gmax) {
 // tid in [0, 320): group g = tid / 20 owns local frames (2g, 2g+1); j = tid % 20.
 
 // Phase 1: window, first 20-point DFT over n1 (samples 20 n1 + j), twiddle, transpose.
-//   s_audio: kAudioTile floats, s_audio[i] = padded sample at tile origin + i
-//   win_half: this thread's 20 window taps, 0.5 * hann[20 n1 + j]
+//   s_audio: kAudioTile samples (float, or raw int16 PCM), s_audio[i] = padded sample at tile origin + i
+//   win_half: this thread's 20 window taps, 0.5 * hann[20 n1 + j] (times 1/32768 for int16 PCM)
 //   s_tw: [j][k1] float2 twiddles exp(-2 pi i j k1 / 400)
 //   s_work: per-group scratch, receives Y[k1][j]
-B200_HD void phase_fft_first(int tid, const float* s_audio, const float (&win_half)[kRadix],
+template <typename InT>
+B200_HD void phase_fft_first(int tid, const InT* s_audio, const float (&win_half)[kRadix],
                              const float2* s_tw, float2* s_work) {
     const int g = tid / kRadix, j = tid % kRadix;
-    const float* fa = s_audio + (2 * g) * kHop + j;
+    const InT* fa = s_audio + (2 * g) * kHop + j;
     float2 x[kRadix], y[kRadix];
 #pragma unroll
     for (int n1 = 0; n1 < kRadix; ++n1)
-        x[n1] = make_float2(fa[kRadix * n1] * win_half[n1], fa[kRadix * n1 + kHop] * win_half[n1]);
+        x[n1] = make_float2(static_cast<float>(fa[kRadix * n1]) * win_half[n1],
+                            static_cast<float>(fa[kRadix * n1 + kHop]) * win_half[n1]);
     dft20(x, y);
     float2* dst = s_work + g * kGroupStride + j;
     dst[0] = y[0];
+    // the twiddle table is symmetric (W^(j k1)); index it [k1][j] so a warp reads consecutive words
 #pragma unroll
-    for (int k1 = 1; k1 < kRadix; ++k1) dst[k1 * kYStride] = cmul(y[k1], s_tw[j * kRadix + k1]);
+    for (int k1 = 1; k1 < kRadix; ++k1) dst[k1 * kYStride] = cmul(y[k1], s_tw[k1 * kRadix + j]);
 }
 
 // Phase 2a: thread k1 = j gathers row k1 of the transpose into registers.
@@ -205,45 +220,57 @@ B200_HD void phase_power_load(int tid, const float2* s_work, float2 (&r)[kRadix]
     }
 }
 
-// Phase 3b: split the packed spectrum and store both frames' power, P[frame][k], k < 200.
-B200_HD void phase_power_store(int tid, const float2 (&r)[kRadix], float2* s_work) {
+// Phase 3b: split the packed spectrum and store both frames' power into the CTA-wide
+// tile P[bin][frame] (bins 0..199, frames 2g and 2g+1 side by side).
+B200_HD void phase_power_store(int tid, const float2 (&r)[kRadix], float* s_P) {
     const int g = tid / kRadix, j = tid % kRadix;
-    float* p = reinterpret_cast<float*>(s_work + g * kGroupStride);
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const float2 zk = r[2 * i], zc = r[2 * i + 1];
         const float are = zk.x + zc.x, aim = zk.y - zc.y;   // 2A[k]/2 (window carries the 1/2)
         const float bre = zk.x - zc.x, bim = zk.y + zc.y;   // |2iB[k]/2| = |B[k]|
         const int k = j + kRadix * i;
-        p[k] = are * are + aim * aim;
-        p[kUsedBins + k] = bre * bre + bim * bim;
+        *reinterpret_cast<float2*>(s_P + k * kPStride + 2 * g) =
+            make_float2(are * are + aim * aim, bre * bre + bim * bim);
     }
 }
 
-// Phase 4: banded mel projection + log10 for both frames of the pair.
-//   s_band: n_mels packed band descriptors; s_melw: packed weights
-//   s_out: [n_mels][kOutStride] staging tile (frames along the row)
-//   returns the max-key of this thread's values over frames < frames_valid
-B200_HD uint32_t phase_mel_log(int tid, int n_mels, const float2* s_work, const int* s_band,
-                               const float* s_melw, float* s_out, int frames_valid) {
-    const int g = tid / kRadix, j = tid % kRadix;
-    const float* p = reinterpret_cast<const float*>(s_work + g * kGroupStride);
+// Phase 4: mel projection as a warp-uniform sweep.  Warp q owns bins [20q, 20q+20), lane f
+// owns frame f, so every lane executes the same program (weights and emit rows are
+// broadcast loads) and the power tile is read along its contiguous frame axis.
+B200_HD void phase_mel_sweep(int tid, const float* s_P, const MelSweepEntry* s_sweep, float* s_S) {
+    const int q = tid >> 5, f = tid & 31;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < kSegBins; ++b) {
+        const int k = q * kSegBins + b;
+        const MelSweepEntry e = s_sweep[k];
+        const float p = s_P[k * kPStride + f];
+        acc0 += e.w0 * p;
+        acc1 += e.w1 * p;
+        const unsigned e0 = e.emit & 0xffffu, e1 = e.emit >> 16;
+        if (e0 != 0xffffu) { s_S[e0 * kSStride + f] = acc0; acc0 = 0.f; }
+        if (e1 != 0xffffu) { s_S[e1 * kSStride + f] = acc1; acc1 = 0.f; }
+    }
+}
+
+// Phase 5: join the partial sums, log10 with the 1e-10 clamp, write the [n_mels, 32] tile
+// (warp = mel row, lane = frame: one 128-byte row segment per store) and return the max key
+// of this thread's valid values.  dst points at out[clip][0][t0]; row_pitch = n_frames.
+B200_HD uint32_t phase_finish(int tid, int n_mels, const float* s_S, const short* s_row_a, const short* s_row_b,
+                              int frames_valid, float* dst, int64_t row_pitch) {
+    const int w = tid >> 5, f = tid & 31;
     uint32_t key = 0u;
-    for (int m = j; m < n_mels; m += kRadix) {
-        const int band = s_band[m];
-        const int first = mel_band_first(band), count = mel_band_count(band);
-        const float* w = s_melw + mel_band_offset(band);
-        float sa = 0.f, sb = 0.f;
-        for (int i = 0; i < count; ++i) {
-            const float wi = w[i];
-            sa += wi * p[first + i];
-            sb += wi * p[kUsedBins + first + i];
-        }
-        const float la = log10_clamped(sa), lb = log10_clamped(sb);
-        s_out[m * kOutStride + 2 * g] = la;
-        s_out[m * kOutStride + 2 * g + 1] = lb;
-        if (2 * g < frames_valid) { const uint32_t ka = max_key_encode(la); key = ka > key ? ka : key; }
-        if (2 * g + 1 < frames_valid) { const uint32_t kb = max_key_encode(lb); key = kb > key ? kb : key; }
+    if (f >= frames_valid) return key;
+    for (int m = w; m < n_mels; m += kWarpsPerCta) {
+        const int ra = s_row_a[m], rb = s_row_b[m];
+        float s = 0.f;
+        if (ra >= 0) s = s_S[ra * kSStride + f];
+        if (rb >= 0) s += s_S[rb * kSStride + f];
+        const float lg = log10_clamped(s);
+        dst[static_cast<int64_t>(m) * row_pitch + f] = lg;
+        const uint32_t k = max_key_encode(lg);
+        key = k > key ? k : key;
     }
     return key;
 }

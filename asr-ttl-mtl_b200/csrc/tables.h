@@ -17,8 +17,13 @@ struct DeviceTables {
     float2 twiddle[kNFFT];          // [j][k1] exp(-2 pi i j k1 / 400)
     float mel_weights[kMaxMelWeights];  // non-zero filter taps, band after band
     int mel_band[kMaxMels];         // mel_band_pack(first bin, taps, offset)
+    // Warp-uniform mel sweep (FFT variant v2): one entry per bin, see phase_mel_sweep.
+    MelSweepEntry sweep[kUsedBins];
+    short row_a[kMaxMels];          // partial-sum row holding the first (or only) part of mel m, -1: empty band
+    short row_b[kMaxMels];          // row of the part that lies in the next 20-bin segment, -1: none
     int n_mels;
     int n_weights;
+    int n_rows;                     // rows of the partial-sum tile S: n_mels + straddling mels
 };
 
 constexpr int kTablesOk = 0;
@@ -52,6 +57,50 @@ inline int build_tables(int n_mels, const float* filters, DeviceTables* t) {
     }
     t->n_mels = n_mels;
     t->n_weights = offset;
+
+    // ---- sweep program: bins are walked in 10 segments of 20; at every bin at most two
+    // mels are active and they are consecutive, so mel m accumulates in slot (m & 1).  A mel
+    // whose band crosses a segment boundary is summed in two parts (rows row_a / row_b).
+    for (int k = 0; k < kUsedBins; ++k) {
+        t->sweep[k].w0 = 0.f; t->sweep[k].w1 = 0.f; t->sweep[k].emit = 0xffffffffu; t->sweep[k].pad = 0;
+    }
+    int n_rows = n_mels;
+    for (int m = 0; m < n_mels; ++m) {
+        t->row_a[m] = -1; t->row_b[m] = -1;
+        const int band = t->mel_band[m];
+        const int first = mel_band_first(band), count = mel_band_count(band);
+        if (count == 0) continue;
+        const int last = first + count - 1;
+        const float* w = t->mel_weights + mel_band_offset(band);
+        const int slot = m & 1;
+        for (int i = 0; i < count; ++i) {
+            float& dst = slot ? t->sweep[first + i].w1 : t->sweep[first + i].w0;
+            if (dst != 0.f) return kTablesBadFilters;  // two active mels of the same parity at one bin
+            dst = w[i];
+        }
+        // the slot must be free again before mel m+2 starts
+        if (m + 2 < n_mels && mel_band_count(t->mel_band[m + 2]) &&
+            mel_band_first(t->mel_band[m + 2]) <= last) return kTablesBadFilters;
+        const int seg_first = first / kSegBins, seg_last = last / kSegBins;
+        if (seg_last - seg_first > 1) return kTablesBadFilters;
+        auto set_emit = [&](int bin, int row) {
+            unsigned e = t->sweep[bin].emit;
+            if (slot) e = (e & 0x0000ffffu) | (static_cast<unsigned>(row) << 16);
+            else e = (e & 0xffff0000u) | static_cast<unsigned>(row);
+            t->sweep[bin].emit = e;
+        };
+        t->row_a[m] = static_cast<short>(m);
+        if (seg_first == seg_last) {
+            set_emit(last, m);
+        } else {
+            if (n_rows >= kMaxSRows) return kTablesBadFilters;
+            set_emit(seg_first * kSegBins + kSegBins - 1, m);
+            t->row_b[m] = static_cast<short>(n_rows);
+            set_emit(last, n_rows);
+            ++n_rows;
+        }
+    }
+    t->n_rows = n_rows;
     return kTablesOk;
 }
 

@@ -90,7 +90,8 @@ size_t b200mel_workspace_bytes(int64_t batch);
  *   right_zero_pad  the `padding` argument (audio.py:145-146); <= 0 is ignored
  *   out        device float32 [batch, n_mels, T] contiguous, T from b200mel_frames
  *   workspace  device scratch of b200mel_workspace_bytes(batch)
- *   l2_chunk_clips  utterances per L2-resident pass (0 = library default)
+ *   l2_chunk_clips  reserved (0): the persistent kernel walks the batch utterance-major, so an
+ *              utterance is normalised while its un-normalised values are still in L2
  */
 int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype, int64_t batch,
                           int64_t n_samples, int64_t stride_b, const int32_t* lengths,

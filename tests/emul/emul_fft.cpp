@@ -25,7 +25,8 @@ extern "C" int emul_fft_logmel(const float* audio, int64_t n_samples, int64_t va
 
     std::vector<float> s_audio(kAudioTile);
     std::vector<float2> s_work(kGroups * kGroupStride);
-    std::vector<float> s_out(n_mels * kOutStride);
+    float* s_P = reinterpret_cast<float*>(s_work.data());  // aliases the FFT scratch, as in the kernel
+    std::vector<float> s_S(tab.n_rows * kSStride);
     std::vector<float2> regs(kThreads * kRadix);
     uint32_t clip_key = 0;
 
@@ -44,21 +45,19 @@ extern "C" int emul_fft_logmel(const float* audio, int64_t n_samples, int64_t va
         for (int tid = 0; tid < kThreads; ++tid) {  // phase 1
             float win_half[kRadix];
             for (int n1 = 0; n1 < kRadix; ++n1) win_half[n1] = tab.win_half[kRadix * n1 + tid % kRadix];
-            phase_fft_first(tid, s_audio.data(), win_half, tab.twiddle, s_work.data());
+            phase_fft_first<float>(tid, s_audio.data(), win_half, tab.twiddle, s_work.data());
         }
         auto R = [&](int tid) -> float2(&)[kRadix] { return *reinterpret_cast<float2(*)[kRadix]>(&regs[tid * kRadix]); };
         for (int tid = 0; tid < kThreads; ++tid) phase_fft_second_load(tid, s_work.data(), R(tid));
         for (int tid = 0; tid < kThreads; ++tid) phase_fft_second_store(tid, R(tid), s_work.data());
         for (int tid = 0; tid < kThreads; ++tid) phase_power_load(tid, s_work.data(), R(tid));
-        for (int tid = 0; tid < kThreads; ++tid) phase_power_store(tid, R(tid), s_work.data());
+        for (int tid = 0; tid < kThreads; ++tid) phase_power_store(tid, R(tid), s_P);
+        for (int tid = 0; tid < kThreads; ++tid) phase_mel_sweep(tid, s_P, tab.sweep, s_S.data());
         const int frames_valid = n_frames - t0 < kTileFrames ? n_frames - t0 : kTileFrames;
         for (int tid = 0; tid < kThreads; ++tid) {
-            const uint32_t k = phase_mel_log(tid, n_mels, s_work.data(), tab.mel_band, tab.mel_weights, s_out.data(), frames_valid);
+            const uint32_t k = phase_finish(tid, n_mels, s_S.data(), tab.row_a, tab.row_b, frames_valid, out + t0, n_frames);
             if (k > clip_key) clip_key = k;
         }
-        for (int m = 0; m < n_mels; ++m)
-            for (int lane = 0; lane < kTileFrames; ++lane)
-                if (t0 + lane < n_frames) out[static_cast<int64_t>(m) * n_frames + t0 + lane] = s_out[m * kOutStride + lane];
     }
     if (do_normalise) {
         const float g = max_key_decode(clip_key);
