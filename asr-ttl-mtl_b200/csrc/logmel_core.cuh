@@ -52,9 +52,10 @@ constexpr int kWarpsPerCta = kThreads / 32;
 static_assert(kSegments == kWarpsPerCta, "one 20-bin segment per warp");
 
 // One bin of the warp-uniform mel sweep.  w0/w1: weight of the active even/odd mel at this
-// bin (0 if none).  emit: low/high 16 bits = S row that receives slot 0/1 after this bin,
-// 0xffff = keep accumulating.
-struct MelSweepEntry { float w0, w1; unsigned emit; int pad; };
+// bin (0 if none).  emit0/emit1: byte offset of the S row that receives slot 0/1 after this
+// bin, negative = keep accumulating.
+struct MelSweepEntry { float w0, w1; int emit0, emit1; };
+B200_HD int s_row_offset(int row) { return row * kSStride * static_cast<int>(sizeof(float)); }
 
 // Packed per-mel band descriptor: first bin | count << 8 | weight offset << 16.
 B200_HD int mel_band_pack(int first, int count, int offset) { return first | (count << 8) | (offset << 16); }
@@ -63,8 +64,41 @@ B200_HD int mel_band_count(int p) { return (p >> 8) & 0xff; }
 B200_HD int mel_band_offset(int p) { return (p >> 16) & 0xffff; }
 
 // ---- complex helpers ---------------------------------------------------------
-B200_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-B200_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// A complex number is a float2 (re, im) living in an aligned register pair, so complex
+// add / subtract / scale map onto Blackwell's packed fp32 instructions (FADD2 / FFMA2 / FMUL2,
+// PTX add/fma/mul.f32x2, sm_100+): one issue slot per complex operation instead of two.
+// The host build (CPU emulator) uses the scalar equivalents; both round to nearest, and the
+// subtraction is an FMA with -1, so the two builds compute the same values.
+B200_HD float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+B200_HD float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a);
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+// a * (s, s): complex times real
+B200_HD float2 cscale(float2 a, float s) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    return __fmul2_rn(a, make_float2(s, s));
+#else
+    return make_float2(a.x * s, a.y * s);
+#endif
+}
+// a * (s, s) + c
+B200_HD float2 cfma(float2 a, float s, float2 c) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    return __ffma2_rn(a, make_float2(s, s), c);
+#else
+    return make_float2(a.x * s + c.x, a.y * s + c.y);
+#endif
+}
 B200_HD float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
 
 // 5-point forward DFT, in place on u[0..4].
@@ -75,11 +109,11 @@ B200_HD void dft5(float2 (&u)[5]) {
     const float s2 = 0.58778525229247313f;   // sin(4 pi / 5)
     const float2 a1 = cadd(u[1], u[4]), b1 = csub(u[1], u[4]);
     const float2 a2 = cadd(u[2], u[3]), b2 = csub(u[2], u[3]);
-    const float2 p1 = make_float2(u[0].x + c1 * a1.x + c2 * a2.x, u[0].y + c1 * a1.y + c2 * a2.y);
-    const float2 p2 = make_float2(u[0].x + c2 * a1.x + c1 * a2.x, u[0].y + c2 * a1.y + c1 * a2.y);
-    const float2 q1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
-    const float2 q2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
-    u[0] = make_float2(u[0].x + a1.x + a2.x, u[0].y + a1.y + a2.y);
+    const float2 p1 = cfma(a2, c2, cfma(a1, c1, u[0]));
+    const float2 p2 = cfma(a2, c1, cfma(a1, c2, u[0]));
+    const float2 q1 = cfma(b2, s2, cscale(b1, s1));
+    const float2 q2 = cfma(b2, -s1, cscale(b1, s2));
+    u[0] = cadd(cadd(u[0], a1), a2);
     // X1 = p1 - i q1, X4 = p1 + i q1, X2 = p2 - i q2, X3 = p2 + i q2
     u[1] = make_float2(p1.x + q1.y, p1.y - q1.x);
     u[4] = make_float2(p1.x - q1.y, p1.y + q1.x);
@@ -146,11 +180,24 @@ B200_HD float max_key_decode(uint32_t k) {
     return bits_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// max that propagates NaN (PTX max.NaN.f32), like torch.max / torch.maximum.
+B200_HD float max_nan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+#else
+    return (a != a || b != b) ? bits_float(0x7fc00000u) : (a > b ? a : b);
+#endif
+}
+
 // log10(max(S, 1e-10)) of audio.py:154; NaN passes through like torch.clamp.
 B200_HD float log10_clamped(float s) {
-    s = (s < 1e-10f) ? 1e-10f : s;
+    s = max_nan(s, 1e-10f);
 #if defined(__CUDA_ARCH__)
-    return __log2f(s) * 0.30102999566398120f;
+    float l2;  // s >= 1e-10 is a normal number: the flush-to-zero form needs no denormal fix-up
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(s));
+    return l2 * 0.30102999566398120f;
 #else
     return __builtin_log2f(s) * 0.30102999566398120f;
 #endif
@@ -226,12 +273,12 @@ B200_HD void phase_power_store(int tid, const float2 (&r)[kRadix], float* s_P) {
     const int g = tid / kRadix, j = tid % kRadix;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const float2 zk = r[2 * i], zc = r[2 * i + 1];
-        const float are = zk.x + zc.x, aim = zk.y - zc.y;   // 2A[k]/2 (window carries the 1/2)
-        const float bre = zk.x - zc.x, bim = zk.y + zc.y;   // |2iB[k]/2| = |B[k]|
+        // A[k] = Z[k] + conj Z[400-k] = (u.x, v.y);  i B[k] = Z[k] - conj Z[400-k] = (v.x, u.y)
+        // (the window table carries the 1/2), so |A|^2 = u.x^2 + v.y^2 and |B|^2 = v.x^2 + u.y^2
+        const float2 u = cadd(r[2 * i], r[2 * i + 1]), v = csub(r[2 * i], r[2 * i + 1]);
         const int k = j + kRadix * i;
         *reinterpret_cast<float2*>(s_P + k * kPStride + 2 * g) =
-            make_float2(are * are + aim * aim, bre * bre + bim * bim);
+            make_float2(u.x * u.x + v.y * v.y, v.x * v.x + u.y * u.y);
     }
 }
 
@@ -240,39 +287,43 @@ B200_HD void phase_power_store(int tid, const float2 (&r)[kRadix], float* s_P) {
 // broadcast loads) and the power tile is read along its contiguous frame axis.
 B200_HD void phase_mel_sweep(int tid, const float* s_P, const MelSweepEntry* s_sweep, float* s_S) {
     const int q = tid >> 5, f = tid & 31;
+    const MelSweepEntry* e = s_sweep + q * kSegBins;
+    const float* p = s_P + q * kSegBins * kPStride + f;
+    char* s_lane = reinterpret_cast<char*>(s_S + f);
     float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
+#pragma unroll
     for (int b = 0; b < kSegBins; ++b) {
-        const int k = q * kSegBins + b;
-        const MelSweepEntry e = s_sweep[k];
-        const float p = s_P[k * kPStride + f];
-        acc0 += e.w0 * p;
-        acc1 += e.w1 * p;
-        const unsigned e0 = e.emit & 0xffffu, e1 = e.emit >> 16;
-        if (e0 != 0xffffu) { s_S[e0 * kSStride + f] = acc0; acc0 = 0.f; }
-        if (e1 != 0xffffu) { s_S[e1 * kSStride + f] = acc1; acc1 = 0.f; }
+        const MelSweepEntry en = e[b];
+        const float pv = p[b * kPStride];
+        acc0 += en.w0 * pv;
+        acc1 += en.w1 * pv;
+        if (en.emit0 >= 0) { *reinterpret_cast<float*>(s_lane + en.emit0) = acc0; acc0 = 0.f; }
+        if (en.emit1 >= 0) { *reinterpret_cast<float*>(s_lane + en.emit1) = acc1; acc1 = 0.f; }
     }
 }
 
 // Phase 5: join the partial sums, log10 with the 1e-10 clamp, write the [n_mels, 32] tile
 // (warp = mel row, lane = frame: one 128-byte row segment per store) and return the max key
 // of this thread's valid values.  dst points at out[clip][0][t0]; row_pitch = n_frames.
-B200_HD uint32_t phase_finish(int tid, int n_mels, const float* s_S, const short* s_row_a, const short* s_row_b,
+// s_row_off[m] / s_row_off[kMaxMels + m]: byte offsets of the (up to) two partial-sum rows of
+// mel m; a missing part points at the all-zero row.
+B200_HD uint32_t phase_finish(int tid, int n_mels, const float* s_S, const int* s_row_off,
                               int frames_valid, float* dst, int64_t row_pitch) {
     const int w = tid >> 5, f = tid & 31;
-    uint32_t key = 0u;
-    if (f >= frames_valid) return key;
+    if (f >= frames_valid) return 0u;
+    const char* s_lane = reinterpret_cast<const char*>(s_S + f);
+    float* out = dst + static_cast<int64_t>(w) * row_pitch + f;
+    const int64_t step = row_pitch * kWarpsPerCta;
+    float mx = bits_float(0xff800000u);  // -inf
     for (int m = w; m < n_mels; m += kWarpsPerCta) {
-        const int ra = s_row_a[m], rb = s_row_b[m];
-        float s = 0.f;
-        if (ra >= 0) s = s_S[ra * kSStride + f];
-        if (rb >= 0) s += s_S[rb * kSStride + f];
+        const float s = *reinterpret_cast<const float*>(s_lane + s_row_off[m]) +
+                        *reinterpret_cast<const float*>(s_lane + s_row_off[kMaxMels + m]);
         const float lg = log10_clamped(s);
-        dst[static_cast<int64_t>(m) * row_pitch + f] = lg;
-        const uint32_t k = max_key_encode(lg);
-        key = k > key ? k : key;
+        *out = lg;
+        out += step;
+        mx = max_nan(mx, lg);
     }
-    return key;
+    return max_key_encode(mx);
 }
 
 }  // namespace b200mel

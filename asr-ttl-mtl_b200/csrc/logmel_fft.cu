@@ -140,7 +140,7 @@ __host__ __device__ constexpr SmemLayout smem_layout(int sample_bytes, int n_row
     l.twiddle = l.s_tile + align16(static_cast<int>(sizeof(float)) * n_rows * kSStride);
     l.sweep = l.twiddle + static_cast<int>(sizeof(float2)) * kNFFT;
     l.rows = l.sweep + static_cast<int>(sizeof(MelSweepEntry)) * kUsedBins;
-    l.total = l.rows + 2 * static_cast<int>(sizeof(short)) * kMaxMels;
+    l.total = l.rows + 2 * static_cast<int>(sizeof(int)) * kMaxMels;
     return l;
 }
 static_assert(sizeof(float) * kUsedBins * kPStride <= sizeof(float2) * kGroups * kGroupStride,
@@ -156,11 +156,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fft_fused_kernel(const Log
     float* s_S = reinterpret_cast<float*>(smem_raw + L.s_tile);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw + L.twiddle);
     MelSweepEntry* s_sweep = reinterpret_cast<MelSweepEntry*>(smem_raw + L.sweep);
-    short* s_row_a = reinterpret_cast<short*>(smem_raw + L.rows);
-    short* s_row_b = s_row_a + kMaxMels;
+    int* s_row_off = reinterpret_cast<int*>(smem_raw + L.rows);
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ int s_next_tile;
     __shared__ int s_norm_clip;
+    __shared__ int s_norm_clip2;  // second slot, only used after the tile loop
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fft_fused_kernel(const Log
     // ---- one-time setup: constant operands -> shared memory / registers, mbarrier ----
     for (int i = tid; i < kNFFT; i += kThreads) s_tw[i] = tab->twiddle[i];
     for (int i = tid; i < kUsedBins; i += kThreads) s_sweep[i] = tab->sweep[i];
-    for (int i = tid; i < kMaxMels; i += kThreads) { s_row_a[i] = tab->row_a[i]; s_row_b[i] = tab->row_b[i]; }
+    for (int i = tid; i < 2 * kMaxMels; i += kThreads) s_row_off[i] = tab->row_off[i];
+    if (tid < kSStride) s_S[(a.n_rows - 1) * kSStride + tid] = 0.f;  // the all-zero row (missing parts)
     float win_half[kRadix];
     {
         const int j = tid % kRadix;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fft_fused_kernel(const Log
     if (tid == 0) {
         mbar_init(&s_mbar, 1);
         s_norm_clip = -1;
+        s_norm_clip2 = -1;
         const unsigned t = atomicAdd(a.tile_counter, 1u);
         s_next_tile = t < total_tiles ? static_cast<int>(t) : -1;
     }
@@ -191,6 +193,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fft_fused_kernel(const Log
 
     int tile = s_next_tile;
     uint32_t parity = 0;
+    int64_t prev_clip = -1;  // utterance of the tile whose completion this warp still has to signal
+    const unsigned warps_per_clip = static_cast<unsigned>(tiles_per_clip) * kWarpsPerCta;
     TileSource src{};
     if (tile >= 0) {
         src = tile_source<InT>(a, tile, tiles_per_clip);
@@ -255,39 +259,54 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fft_fused_kernel(const Log
             __syncthreads();  // #5
             phase_mel_sweep(tid, s_P, s_sweep, s_S);
             __syncthreads();  // #6
-            key = phase_finish(tid, a.n_mels, s_S, s_row_a, s_row_b, frames_valid, dst, a.n_frames);
         } else {
             __syncthreads();  // keeps s_norm_clip's reset ordered like the main path
             if (tid == 0 && norm_clip >= 0) s_norm_clip = -1;
-            // a tile of pure tail zeros: every value is log10(1e-10), computed by the same code
-            const float floor_lg = log10_clamped(0.f);
-            if (lane < frames_valid) {
-                for (int m = warp; m < a.n_mels; m += kWarpsPerCta) dst[static_cast<int64_t>(m) * a.n_frames + lane] = floor_lg;
-                key = max_key_encode(floor_lg);
-            }
             __syncthreads();
         }
 
-        // per-utterance max (warp REDUX + one atomic per warp), then the completion count
-        key = __reduce_max_sync(0xffffffffu, key);
-        const int64_t key_slot = a.global_max ? 0 : src.clip;
-        if (lane == 0) atomicMax(a.max_keys + key_slot, key);
-        if (a.fused_norm) {
-            __threadfence();  // this warp's tile rows and its max are visible before it is counted
-            if (lane == 0) {
-                const unsigned done = atomicAdd(a.done_counters + src.clip, 1u);
-                if (done == static_cast<unsigned>(tiles_per_clip) * kWarpsPerCta - 1u) s_norm_clip = static_cast<int>(src.clip);
-            }
+        // Completion signal of the PREVIOUS tile, one pass late: its stores drained long ago, so the
+        // fence is cheap, and the counter's old value is not needed until this tile's stores are out.
+        unsigned done_before = 0;
+        if (a.fused_norm && prev_clip >= 0) {
+            __threadfence();  // the previous tile's rows and max are visible before it is counted
+            if (lane == 0) done_before = atomicAdd(a.done_counters + prev_clip, 1u);
         }
+
+        if (!src.all_zero) {
+            key = phase_finish(tid, a.n_mels, s_S, s_row_off, frames_valid, dst, a.n_frames);
+        } else if (lane < frames_valid) {
+            // a tile of pure tail zeros: every value is log10(1e-10), computed by the same code
+            const float floor_lg = log10_clamped(0.f);
+            for (int m = warp; m < a.n_mels; m += kWarpsPerCta) dst[static_cast<int64_t>(m) * a.n_frames + lane] = floor_lg;
+            key = max_key_encode(floor_lg);
+        }
+
+        // per-utterance max: warp REDUX + one atomic per warp
+        key = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0) {
+            atomicMax(a.max_keys + (a.global_max ? 0 : src.clip), key);
+            if (a.fused_norm && prev_clip >= 0 && done_before == warps_per_clip - 1u) s_norm_clip = static_cast<int>(prev_clip);
+        }
+        prev_clip = src.clip;
         tile = next;
         src = nsrc;
     }
 
+    // signal the last tile, then pick up an utterance that this CTA completed at the very end
+    if (a.fused_norm && prev_clip >= 0) {
+        __threadfence();
+        if (lane == 0) {
+            const unsigned done_before = atomicAdd(a.done_counters + prev_clip, 1u);
+            if (done_before == warps_per_clip - 1u) s_norm_clip2 = static_cast<int>(prev_clip);
+        }
+    }
     __syncthreads();
-    if (s_norm_clip >= 0) {
-        const int norm_clip = s_norm_clip;
-        const float g = max_key_decode(__ldcg(a.max_keys + norm_clip));
-        normalise_clip(a.out + static_cast<int64_t>(norm_clip) * elems_per_clip, elems_per_clip, g, tid);
+    for (int k = 0; k < 2; ++k) {
+        const int pending = k == 0 ? s_norm_clip : s_norm_clip2;
+        if (pending < 0) continue;
+        const float g = max_key_decode(__ldcg(a.max_keys + pending));
+        normalise_clip(a.out + static_cast<int64_t>(pending) * elems_per_clip, elems_per_clip, g, tid);
     }
 }
 

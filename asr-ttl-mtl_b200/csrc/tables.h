@@ -19,11 +19,11 @@ struct DeviceTables {
     int mel_band[kMaxMels];         // mel_band_pack(first bin, taps, offset)
     // Warp-uniform mel sweep (FFT variant v2): one entry per bin, see phase_mel_sweep.
     MelSweepEntry sweep[kUsedBins];
-    short row_a[kMaxMels];          // partial-sum row holding the first (or only) part of mel m, -1: empty band
-    short row_b[kMaxMels];          // row of the part that lies in the next 20-bin segment, -1: none
+    int row_off[2 * kMaxMels];      // byte offsets of the two partial-sum rows of mel m ([m], [kMaxMels + m]);
+                                    // a missing part points at the all-zero row (index n_rows - 1)
     int n_mels;
     int n_weights;
-    int n_rows;                     // rows of the partial-sum tile S: n_mels + straddling mels
+    int n_rows;                     // rows of the partial-sum tile S: n_mels + straddling mels + 1 zero row
 };
 
 constexpr int kTablesOk = 0;
@@ -62,11 +62,12 @@ inline int build_tables(int n_mels, const float* filters, DeviceTables* t) {
     // mels are active and they are consecutive, so mel m accumulates in slot (m & 1).  A mel
     // whose band crosses a segment boundary is summed in two parts (rows row_a / row_b).
     for (int k = 0; k < kUsedBins; ++k) {
-        t->sweep[k].w0 = 0.f; t->sweep[k].w1 = 0.f; t->sweep[k].emit = 0xffffffffu; t->sweep[k].pad = 0;
+        t->sweep[k].w0 = 0.f; t->sweep[k].w1 = 0.f; t->sweep[k].emit0 = -1; t->sweep[k].emit1 = -1;
     }
     int n_rows = n_mels;
+    int row_a[kMaxMels], row_b[kMaxMels];
     for (int m = 0; m < n_mels; ++m) {
-        t->row_a[m] = -1; t->row_b[m] = -1;
+        row_a[m] = -1; row_b[m] = -1;
         const int band = t->mel_band[m];
         const int first = mel_band_first(band), count = mel_band_count(band);
         if (count == 0) continue;
@@ -84,21 +85,23 @@ inline int build_tables(int n_mels, const float* filters, DeviceTables* t) {
         const int seg_first = first / kSegBins, seg_last = last / kSegBins;
         if (seg_last - seg_first > 1) return kTablesBadFilters;
         auto set_emit = [&](int bin, int row) {
-            unsigned e = t->sweep[bin].emit;
-            if (slot) e = (e & 0x0000ffffu) | (static_cast<unsigned>(row) << 16);
-            else e = (e & 0xffff0000u) | static_cast<unsigned>(row);
-            t->sweep[bin].emit = e;
+            (slot ? t->sweep[bin].emit1 : t->sweep[bin].emit0) = s_row_offset(row);
         };
-        t->row_a[m] = static_cast<short>(m);
+        row_a[m] = m;
         if (seg_first == seg_last) {
             set_emit(last, m);
         } else {
-            if (n_rows >= kMaxSRows) return kTablesBadFilters;
+            if (n_rows >= kMaxSRows - 1) return kTablesBadFilters;
             set_emit(seg_first * kSegBins + kSegBins - 1, m);
-            t->row_b[m] = static_cast<short>(n_rows);
+            row_b[m] = n_rows;
             set_emit(last, n_rows);
             ++n_rows;
         }
+    }
+    const int zero_row = n_rows++;
+    for (int m = 0; m < kMaxMels; ++m) {
+        t->row_off[m] = s_row_offset(m < n_mels && row_a[m] >= 0 ? row_a[m] : zero_row);
+        t->row_off[kMaxMels + m] = s_row_offset(m < n_mels && row_b[m] >= 0 ? row_b[m] : zero_row);
     }
     t->n_rows = n_rows;
     return kTablesOk;

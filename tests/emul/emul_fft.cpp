@@ -26,7 +26,7 @@ extern "C" int emul_fft_logmel(const float* audio, int64_t n_samples, int64_t va
     std::vector<float> s_audio(kAudioTile);
     std::vector<float2> s_work(kGroups * kGroupStride);
     float* s_P = reinterpret_cast<float*>(s_work.data());  // aliases the FFT scratch, as in the kernel
-    std::vector<float> s_S(tab.n_rows * kSStride);
+    std::vector<float> s_S(tab.n_rows * kSStride, 0.f);  // last row is the all-zero row
     std::vector<float2> regs(kThreads * kRadix);
     uint32_t clip_key = 0;
 
@@ -55,7 +55,7 @@ extern "C" int emul_fft_logmel(const float* audio, int64_t n_samples, int64_t va
         for (int tid = 0; tid < kThreads; ++tid) phase_mel_sweep(tid, s_P, tab.sweep, s_S.data());
         const int frames_valid = n_frames - t0 < kTileFrames ? n_frames - t0 : kTileFrames;
         for (int tid = 0; tid < kThreads; ++tid) {
-            const uint32_t k = phase_finish(tid, n_mels, s_S.data(), tab.row_a, tab.row_b, frames_valid, out + t0, n_frames);
+            const uint32_t k = phase_finish(tid, n_mels, s_S.data(), tab.row_off, frames_valid, out + t0, n_frames);
             if (k > clip_key) clip_key = k;
         }
     }
