@@ -68,6 +68,7 @@ struct b200mel_plan {
     int n_mels = 0;
     int n_rows = 0;  // rows of the mel partial-sum tile (DeviceTables::n_rows)
     b200mel::DeviceTables* d_tables = nullptr;
+    b200mel::TcTables* d_tc_tables = nullptr;  // operands of the tcgen05 variant
     std::mutex host_mutex;  // the host pipeline's staging buffers are per plan
     b200mel::HostSlot slots[b200mel::kHostSlots];
 };
@@ -175,6 +176,9 @@ int b200mel_plan_create(int n_mels, const float* filters_host, b200mel_plan** pl
     std::vector<DeviceTables> host(1);
     const int st = build_tables(n_mels, filters_host, host.data());
     if (st != B200MEL_OK) return st;
+    std::vector<TcTables> tc_host(1);
+    const int st_tc = build_tc_tables(n_mels, filters_host, tc_host.data());
+    if (st_tc != B200MEL_OK) return st_tc;
     b200mel_plan* plan = new (std::nothrow) b200mel_plan();
     if (plan == nullptr) return B200MEL_ERR_BAD_ARGUMENT;
     plan->n_mels = n_mels;
@@ -182,7 +186,10 @@ int b200mel_plan_create(int n_mels, const float* filters_host, b200mel_plan** pl
     cudaError_t e = cudaGetDevice(&plan->device);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&plan->d_tables), sizeof(DeviceTables));
     if (e == cudaSuccess) e = cudaMemcpy(plan->d_tables, host.data(), sizeof(DeviceTables), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&plan->d_tc_tables), sizeof(TcTables));
+    if (e == cudaSuccess) e = cudaMemcpy(plan->d_tc_tables, tc_host.data(), sizeof(TcTables), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
+        if (plan->d_tc_tables) cudaFree(plan->d_tc_tables);
         if (plan->d_tables) cudaFree(plan->d_tables);
         delete plan;
         return cuda_fail(e, "b200mel_plan_create");
@@ -194,6 +201,7 @@ int b200mel_plan_create(int n_mels, const float* filters_host, b200mel_plan** pl
 int b200mel_plan_destroy(b200mel_plan* plan) {
     if (plan == nullptr) return B200MEL_OK;
     for (auto& s : plan->slots) free_slot(s);
+    if (plan->d_tc_tables) cudaFree(plan->d_tc_tables);
     if (plan->d_tables) cudaFree(plan->d_tables);
     delete plan;
     return B200MEL_OK;
@@ -223,8 +231,8 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     if (plan == nullptr || out == nullptr || workspace == nullptr) return B200MEL_ERR_NULL_POINTER;
     if (dtype != B200MEL_F32 && dtype != B200MEL_S16) return B200MEL_ERR_BAD_ARGUMENT;
     if (batch < 0 || n_samples < 0 || stride_b < 0 || l2_chunk_clips < 0) return B200MEL_ERR_BAD_ARGUMENT;
-    if (variant == B200MEL_VARIANT_AUTO) variant = B200MEL_VARIANT_FFT;
-    if (variant != B200MEL_VARIANT_FFT) return B200MEL_ERR_BAD_ARGUMENT;
+    if (variant == B200MEL_VARIANT_AUTO) variant = B200MEL_VARIANT_FFT;  // the variant ncu picked, see DESIGN.md
+    if (variant != B200MEL_VARIANT_FFT && variant != B200MEL_VARIANT_TCGEN05) return B200MEL_ERR_BAD_ARGUMENT;
     int64_t n_frames = 0;
     const int st = b200mel_frames(n_samples, right_zero_pad, &n_frames);
     if (st != B200MEL_OK) return st;
@@ -256,10 +264,13 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     a.done_counters = keys + batch;
     a.tile_counter = keys + 2 * batch;
     a.global_max = global_max;
-    a.fused_norm = (!global_max && tiles_per_clip <= kMaxFusedNormTiles) ? 1 : 0;
+    a.fused_norm = (variant == B200MEL_VARIANT_FFT && !global_max && tiles_per_clip <= kMaxFusedNormTiles) ? 1 : 0;
     a.n_rows = plan->n_rows;
     a.tables = plan->d_tables;
-    B200_CUDA(launch_fft_fused(a, dtype, stream));
+    if (variant == B200MEL_VARIANT_TCGEN05)
+        B200_CUDA(launch_tc_pass1(a, plan->d_tc_tables, dtype, stream));
+    else
+        B200_CUDA(launch_fft_fused(a, dtype, stream));
     if (!a.fused_norm) B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, global_max, stream));
     return B200MEL_OK;
 }

@@ -20,8 +20,13 @@
 #define B200_HD __host__ __device__ __forceinline__
 #else
 #define B200_HD inline
+#if defined(B200_HOST_HAS_CUDA_HEADERS)  // host build that also pulls in CUDA's own vector types
+#include <vector_functions.h>
+#include <vector_types.h>
+#else
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+#endif
 #endif
 
 namespace b200mel {

@@ -83,6 +83,37 @@ def emul():
 
 
 @pytest.fixture(scope="session")
+def emul_tc():
+    """CPU emulator of the tcgen05 variant (tests/emul/emul_tc.cpp)."""
+    src = os.path.join(EMUL_DIR, "emul_tc.cpp")
+    lib = os.path.join(EMUL_DIR, "libemul_tc.so")
+    csrc = os.path.join(ROOT, "asr-ttl-mtl_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("logmel_core.cuh", "tables.h", "tc_core.cuh", "tc_tables.h")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-Wno-strict-aliasing",
+                        "-DB200_HOST_HAS_CUDA_HEADERS", "-I/usr/local/cuda/include", "-o", lib, src], check=True)
+    h = ctypes.CDLL(lib)
+    fp = ctypes.POINTER(ctypes.c_float)
+    h.emul_tc_logmel.argtypes = [fp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, fp, fp, ctypes.c_int]
+    h.emul_tc_logmel.restype = ctypes.c_int
+    h.emul_fft16_real_x2.argtypes = [fp, fp]
+
+    def run(x, n_mels, filters, padding=0, valid=None, normalise=True):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        frames = (n + max(padding, 0)) // 160
+        out = np.zeros((n_mels, frames), np.float32)
+        f = np.ascontiguousarray(filters, dtype=np.float32)
+        st = h.emul_tc_logmel(x.ctypes.data_as(fp), n, n if valid is None else valid, padding, n_mels,
+                              f.ctypes.data_as(fp), out.ctypes.data_as(fp), int(normalise))
+        assert st == 0, f"emulator status {st}"
+        return out
+
+    h.run = run
+    return h
+
+
+@pytest.fixture(scope="session")
 def native_lib():
     """libb200mel.so, built in-tree by nvcc (cross-compiles without a GPU)."""
     import __graft_entry__ as entry

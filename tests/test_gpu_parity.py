@@ -13,7 +13,7 @@ from oracle import signals
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 DEV = "cuda:0"
-VARIANTS = ["fft"]
+VARIANTS = ["fft", "tcgen05"]
 
 
 def _maxerr(a, b):
@@ -54,6 +54,39 @@ def test_batch_is_per_utterance_stack_of_oracle_calls(b200, n_mels, variant):
     # adversarial signals: stay as close to the float64 spec as the reference does (+5e-5)
     for i, k in enumerate(kinds):
         assert _maxerr(got[i], f64[i]) <= _maxerr(want[i], f64[i]) + 5e-5, k
+
+
+def test_tcgen05_variant_golden_cases(b200, golden):
+    worst = 0.0
+    for c in golden.cases:
+        x = torch.from_numpy(golden.signal(c)).to(DEV)[None]
+        got = b200.log_mel_spectrogram_batch(x, n_mels=c["n_mels"], padding=c["padding"], variant="tcgen05")[0]
+        assert tuple(got.shape) == tuple(c["shape"])
+        err = _maxerr(got, golden.out(c))
+        worst = max(worst, err)
+        assert err <= TOL, (c, err)
+    print(f"worst golden error (tcgen05) {worst:.3e}")
+
+
+def test_tcgen05_variant_lengths_pcm16_and_full_batch(b200):
+    lens = np.array([0, 201, 16000, 47999, 48000, 52000], dtype=np.int64)
+    rows = np.stack([signals.make_signal("gauss", 48000, 900 + i) for i in range(len(lens))])
+    padded = rows.copy()
+    for i, n in enumerate(lens):
+        padded[i, min(n, 48000):] = 0.0
+    a = b200.log_mel_spectrogram_batch(torch.from_numpy(rows).to(DEV), lengths=torch.from_numpy(lens), variant="tcgen05")
+    b = b200.log_mel_spectrogram_batch(torch.from_numpy(padded).to(DEV), variant="tcgen05")
+    assert torch.equal(a, b) and torch.all(a[0] == -1.5)
+    assert _maxerr(a, orc.logmel_f32_port_per_utterance(torch.from_numpy(padded), 80)) <= TOL
+    q = np.stack([signals.make_pcm16(32000, 60 + i) for i in range(3)])
+    f = q.astype(np.float32) / 32768.0
+    assert torch.equal(b200.log_mel_spectrogram_batch(torch.from_numpy(q).to(DEV), n_mels=128, variant="tcgen05"),
+                       b200.log_mel_spectrogram_batch(torch.from_numpy(f).to(DEV), n_mels=128, variant="tcgen05"))
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    audio = (0.1 * torch.randn(64, 480000, generator=gen, device=DEV)).clamp_(-1, 1)
+    tc = b200.log_mel_spectrogram_batch(audio, variant="tcgen05")
+    fft = b200.log_mel_spectrogram_batch(audio, variant="fft")
+    assert _maxerr(tc, fft) <= TOL and torch.isfinite(tc).all()
 
 
 def test_reference_2d_semantics_one_max_per_call(b200, golden):
