@@ -188,19 +188,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelAr
                 valid = len < 0 ? 0 : (len < valid ? len : valid);
             }
             const int64_t s0 = static_cast<int64_t>(t0) * kHop - kHalfWin;
-            if (s0 >= 0 && s0 + kTcAudioSamples <= valid) {
+            if (sizeof(InT) == 4 && s0 >= 0 && s0 + kTcAudioSamples <= valid) {
+                // interior tile: asynchronous 4-byte copies, one 160-sample row per warp pass (rows land at pitch 161)
                 const InT* __restrict__ src = row + s0;
-                for (int i = tid; i < kTcAudioSamples; i += kTcThreads) s_audio[i + i / kHop] = sample_to_float<InT>(__ldg(src + i));
-            } else {
-                for (int i = tid; i < kTcAudioSamples; i += kTcThreads) {
-                    const int64_t pos = s0 + i;
-                    float v = 0.f;
-                    if (pos < a.total + kHalfWin) {
-                        const int64_t idx = reflect_source_index(pos, a.total);
-                        if (idx >= 0 && idx < valid) v = sample_to_float<InT>(__ldg(row + idx));
-                    }
-                    s_audio[i + i / kHop] = v;
+                for (int r = warp; r < kTcAudioRows; r += kTcThreads / 32) {
+                    const int cols = r == kTcAudioRows - 1 ? kTcAudioSamples - kHop * (kTcAudioRows - 1) : kHop;
+                    const uint32_t dst = smem_u32(s_audio + r * kTcRowPitch);
+                    const InT* g = src + r * kHop;
+#pragma unroll
+                    for (int c = lane; c < kHop; c += 32)
+                        if (c < cols) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(g + c) : "memory");
                 }
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+            } else {
+                for (int r = warp; r < kTcAudioRows; r += kTcThreads / 32)
+                    for (int c = lane; c < kHop; c += 32) {
+                        const int i = r * kHop + c;
+                        float v = 0.f;
+                        if (i < kTcAudioSamples) {
+                            const int64_t pos = s0 + i;
+                            if (pos < a.total + kHalfWin) {
+                                const int64_t idx = reflect_source_index(pos, a.total);
+                                if (idx >= 0 && idx < valid) v = sample_to_float<InT>(__ldg(row + idx));
+                            }
+                        }
+                        s_audio[r * kTcRowPitch + c] = v;
+                    }
             }
         }
         __syncthreads();

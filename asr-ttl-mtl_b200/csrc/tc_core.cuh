@@ -138,15 +138,20 @@ B200_HD void tc_stage1(const float* frame_audio, int n2, const float (&win)[16],
 }
 
 // Epilogue of one unit for one thread: 16 complex outputs -> power -> accumulate this thread's
-// parity taps into its column of the S tile (s_col points at S[0][frame]).
+// parity taps into its column of the S tile (s_col points at S[0][frame]).  The 16 taps of a unit
+// never alias (tc_tables.h), so all loads are issued before the stores.
 B200_HD void tc_accumulate(const float (&d)[32], const TcTap* taps, char* s_col) {
+    float acc[16];
+    int off[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const TcTap t = taps[j];
+        off[j] = t.s_off;
         const float p = d[2 * j] * d[2 * j] + d[2 * j + 1] * d[2 * j + 1];
-        float* s = reinterpret_cast<float*>(s_col + t.s_off);
-        *s += t.w * p;
+        acc[j] = *reinterpret_cast<const float*>(s_col + t.s_off) + t.w * p;
     }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(s_col + off[j]) = acc[j];
 }
 
 }  // namespace b200mel

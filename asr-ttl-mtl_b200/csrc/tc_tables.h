@@ -12,15 +12,20 @@ namespace b200mel {
 // index of element (n, k) in a K-major, no-swizzle tcgen05 operand of kTcN rows: strips [k/8][n][8]
 inline int tc_operand_index(int n, int k) { return (k / 8) * (kTcN * 8) + n * 8 + (k % 8); }
 
-// bins produced by block 0, in output order: X[16 j] (j = 1..12) from Y[0,.], X[8 + 16 j] (j = 0..11) from Y[8,.]
-inline int tc_block0_bin(int c) { return c < 12 ? 16 * (c + 1) : 8 + 16 * (c - 12); }
-
-// bin (0..199) of complex output c of block b, or -1 if that output is padding
-inline int tc_output_bin(int b, int c) {
-    if (b == 0) return c < 24 ? tc_block0_bin(c) : -1;
-    if (c >= kTcN2) return -1;
-    const int k = b + 16 * c;
-    return k <= 199 ? k : kNFFT - k;  // |X[400-k]| = |X[k]| for real input
+// Output order of a block: N-half h, slot j (0..15).  Within one half no two bins share a mel (they are
+// 16 bins apart and no filter is that wide), so an epilogue thread can pipeline its 16 tap updates.
+//   block 0 : half 0 = X[16 (j+1)] (j < 12, from Y[0,.]);  half 1 = X[8 + 16 j] (j < 12, from Y[8,.])
+//   block b : half 0 = X[b + 16 j] (j < 13, bins <= 199);  half 1 = X[b + 16 (13 + j)] (j < 12), mirrored to 400 - k
+// Returns the DFT index k (0..399) or -1 for a padding slot.
+inline int tc_output_k(int b, int h, int j) {
+    if (b == 0) return j < 12 ? (h == 0 ? 16 * (j + 1) : 8 + 16 * j) : -1;
+    if (h == 0) return j < 13 ? b + 16 * j : -1;
+    return j < 12 ? b + 16 * (13 + j) : -1;
+}
+// bin (1..199) that slot feeds: |X[400-k]| = |X[k]| for real input
+inline int tc_output_bin(int b, int h, int j) {
+    const int k = tc_output_k(b, h, j);
+    return k < 0 ? -1 : (k <= 199 ? k : kNFFT - k);
 }
 
 // filters: float32 [n_mels, 201] row-major.  Returns kTablesOk or kTablesBadFilters.
@@ -38,23 +43,29 @@ inline int build_tc_tables(int n_mels, const float* filters, TcTables* t) {
             t->tw[n2][b] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
         }
     }
-    // dense stage-2 matrices B[k = (n2, re|im)][n = (output c, re|im)], float64
+    // dense stage-2 matrices B[k = (n2, re|im)][n = 32 h + 2 j + (re|im)], float64.
+    // X[k] = sum_n2 In[n2] exp(-2 pi i n2 k / 400) * (twiddle already applied for blocks 1..7, so the
+    // remaining factor there is W25^(n2 k2) = exp(-2 pi i n2 (k - b) / 400)).
     static double B[2][50][kTcN];
     std::memset(B, 0, sizeof(B));
-    for (int n2 = 0; n2 < kTcN2; ++n2) {
-        for (int c = 0; c < kTcN2; ++c) {  // blocks 1..7: (a + i b)(cos - i sin)
-            const double th = two_pi * n2 * c / 25.0, cs = std::cos(th), sn = std::sin(th);
-            B[1][2 * n2][2 * c] = cs;      B[1][2 * n2 + 1][2 * c] = sn;
-            B[1][2 * n2][2 * c + 1] = -sn; B[1][2 * n2 + 1][2 * c + 1] = cs;
-        }
-        for (int c = 0; c < 24; ++c) {     // block 0: real inputs Y0 (row 2 n2) and Y8 (row 2 n2 + 1)
-            const int k = tc_block0_bin(c);
-            const double th = two_pi * n2 * k / kNFFT;  // W25^(n2 k2) for k = 16 k2; carries W400^(8 n2) for k = 8 + 16 k2
-            const int row = c < 12 ? 2 * n2 : 2 * n2 + 1;
-            B[0][row][2 * c] = std::cos(th);
-            B[0][row][2 * c + 1] = -std::sin(th);
-        }
-    }
+    for (int n2 = 0; n2 < kTcN2; ++n2)
+        for (int h = 0; h < 2; ++h)
+            for (int j = 0; j < 16; ++j) {
+                const int col = 32 * h + 2 * j;
+                int k = tc_output_k(1, h, j);            // blocks 1..7 share one matrix: use b = 1, k2 = (k - 1) / 16
+                if (k >= 0) {
+                    const double th = two_pi * n2 * ((k - 1) / 16) / 25.0, cs = std::cos(th), sn = std::sin(th);
+                    B[1][2 * n2][col] = cs;      B[1][2 * n2 + 1][col] = sn;       // (a + i b)(cos - i sin)
+                    B[1][2 * n2][col + 1] = -sn; B[1][2 * n2 + 1][col + 1] = cs;
+                }
+                k = tc_output_k(0, h, j);                // block 0: real inputs Y0 (row 2 n2) / Y8 (row 2 n2 + 1)
+                if (k >= 0) {
+                    const double th = two_pi * n2 * k / kNFFT;
+                    const int row = h == 0 ? 2 * n2 : 2 * n2 + 1;
+                    B[0][row][col] = std::cos(th);
+                    B[0][row][col + 1] = -std::sin(th);
+                }
+            }
     for (int set = 0; set < 2; ++set)
         for (int n = 0; n < kTcN; ++n)
             for (int k = 0; k < 50; ++k) {
@@ -72,7 +83,7 @@ inline int build_tc_tables(int n_mels, const float* filters, TcTables* t) {
                 TcTap tap;
                 tap.w = 0.f;
                 tap.s_off = (n_mels + p) * row_bytes;  // scratch row of this parity
-                const int bin = tc_output_bin(u / 2, 16 * (u % 2) + j);
+                const int bin = tc_output_bin(u / 2, u % 2, j);
                 if (bin >= 0) {
                     int found = 0;
                     for (int m = p; m < n_mels; m += 2) {
