@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200mel.so")
 
 SOURCES = ["b200mel_api.cu", "logmel_fft.cu", "logmel_tc.cu"]
-HEADERS = ["kernels.h", "logmel_core.cuh", "tables.h", "tc_core.cuh", "tc_tables.h", os.path.join(ROOT, "include", "b200mel.h")]
+HEADERS = ["kernels.h", "logmel_core.cuh", "tables.h", "tc_core.cuh", "tc_tables.h", "mel_bands.h", os.path.join(ROOT, "include", "b200mel.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -68,7 +68,8 @@ struct b200mel_plan {
     int n_mels = 0;
     int n_rows = 0;  // rows of the mel partial-sum tile (DeviceTables::n_rows)
     b200mel::DeviceTables* d_tables = nullptr;
-    b200mel::TcTables* d_tc_tables = nullptr;  // operands of the tcgen05 variant
+    b200mel::TcTables* d_tc_tables = nullptr;  // operands of the tcgen05 variant (nullptr: the filter matrix is not the
+                                               // Whisper bank that variant's epilogue is compiled for)
     std::mutex host_mutex;  // the host pipeline's staging buffers are per plan
     b200mel::HostSlot slots[b200mel::kHostSlots];
 };
@@ -177,8 +178,7 @@ int b200mel_plan_create(int n_mels, const float* filters_host, b200mel_plan** pl
     const int st = build_tables(n_mels, filters_host, host.data());
     if (st != B200MEL_OK) return st;
     std::vector<TcTables> tc_host(1);
-    const int st_tc = build_tc_tables(n_mels, filters_host, tc_host.data());
-    if (st_tc != B200MEL_OK) return st_tc;
+    const bool tc_ok = build_tc_tables(n_mels, filters_host, tc_host.data()) == B200MEL_OK;
     b200mel_plan* plan = new (std::nothrow) b200mel_plan();
     if (plan == nullptr) return B200MEL_ERR_BAD_ARGUMENT;
     plan->n_mels = n_mels;
@@ -186,8 +186,10 @@ int b200mel_plan_create(int n_mels, const float* filters_host, b200mel_plan** pl
     cudaError_t e = cudaGetDevice(&plan->device);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&plan->d_tables), sizeof(DeviceTables));
     if (e == cudaSuccess) e = cudaMemcpy(plan->d_tables, host.data(), sizeof(DeviceTables), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&plan->d_tc_tables), sizeof(TcTables));
-    if (e == cudaSuccess) e = cudaMemcpy(plan->d_tc_tables, tc_host.data(), sizeof(TcTables), cudaMemcpyHostToDevice);
+    if (tc_ok) {
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&plan->d_tc_tables), sizeof(TcTables));
+        if (e == cudaSuccess) e = cudaMemcpy(plan->d_tc_tables, tc_host.data(), sizeof(TcTables), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         if (plan->d_tc_tables) cudaFree(plan->d_tc_tables);
         if (plan->d_tables) cudaFree(plan->d_tables);
@@ -233,6 +235,7 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     if (batch < 0 || n_samples < 0 || stride_b < 0 || l2_chunk_clips < 0) return B200MEL_ERR_BAD_ARGUMENT;
     if (variant == B200MEL_VARIANT_AUTO) variant = B200MEL_VARIANT_FFT;  // the variant ncu picked, see DESIGN.md
     if (variant != B200MEL_VARIANT_FFT && variant != B200MEL_VARIANT_TCGEN05) return B200MEL_ERR_BAD_ARGUMENT;
+    if (variant == B200MEL_VARIANT_TCGEN05 && plan->d_tc_tables == nullptr) return B200MEL_ERR_BAD_FILTERS;
     int64_t n_frames = 0;
     const int st = b200mel_frames(n_samples, right_zero_pad, &n_frames);
     if (st != B200MEL_OK) return st;

@@ -32,8 +32,8 @@ struct LogmelArgs {
 // FFT variant, one persistent launch: log10 mel + per-utterance max keys (+ in-place normalise when
 // a.fused_norm).  The counters in `a` must be zero when the kernel starts.
 cudaError_t launch_fft_fused(const LogmelArgs& a, int dtype, cudaStream_t stream);
-// tcgen05 variant: log10 mel + per-utterance max keys (stage 2 of the DFT on the tensor cores);
-// always followed by launch_normalise.
+// tcgen05 variant: log10 mel + per-utterance max keys (the folded DFT as GEMMs on the tensor cores);
+// always followed by launch_normalise.  tables: device copy of the constant matrices.
 cudaError_t launch_tc_pass1(const LogmelArgs& a, const TcTables* tables, int dtype, cudaStream_t stream);
 // Pass 2 (shared by all variants): out = (max(out, g - 8) + 4) / 4.
 cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip,

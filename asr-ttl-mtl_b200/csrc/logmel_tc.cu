@@ -1,22 +1,29 @@
-// tcgen05 (tensor-core) variant of the fused log-mel front-end for sm_100a — DFT-as-GEMM with
-// split-precision compensation (reference: whisper/audio.py:145-155; math in tc_core.cuh).
+// tcgen05 (tensor-core) variant of the fused log-mel front-end for sm_100a: the folded DFT as four
+// 128 x 104 x 112 GEMMs per 128-frame tile, 3-product fp16 split precision (math: tc_core.cuh;
+// reference: whisper/audio.py:145-155).
 //
-// One persistent CTA per SM, 128 frames (= 128 tensor-memory lanes = MMA M) per tile:
-//   1. the tile's 20720 samples are staged in shared memory (rows of 160 at pitch 161, so the
-//      frame-per-thread reads below are bank-conflict free);
-//   2. 8 worker warps (two per TMEM lane quadrant) run stage 1 on the CUDA cores — windowed real
-//      FFT-16 over the 25 strided sub-sequences of every frame, twiddle, fp16 hi/lo split — and
-//      write the result straight into TENSOR MEMORY as the A operand (tcgen05.st, one 32-bit column
-//      = one packed complex value; 8 blocks x [25 hi | 25 lo | 6 zero] columns);
-//   3. one elected thread issues stage 2 on the tensor cores: per (block, N-half) unit 7 + 4
-//      tcgen05.mma.kind::f16 (A from TMEM, B = the shared DFT-25 matrix [Bhi; Bhi] / [Blo] from shared
-//      memory, fp32 accumulator in TMEM), i.e. hi*Bhi + lo*Bhi + hi*Blo; accumulators are double
-//      buffered and handed over with tcgen05.commit -> mbarrier;
-//   4. the workers read each accumulator (tcgen05.ld), form the power of 16 bins and add their mel
-//      taps into a [n_mels, 128] tile in shared memory (two warps per quadrant own even / odd mels);
-//   5. log10(max(.,1e-10)), 128-byte coalesced row stores, per-utterance max key.
-// The (max-8, (x+4)/4) step runs as the shared pass-2 kernel.
+// One persistent CTA per SM, warp-specialised, no __syncthreads in the steady state (mbarriers only):
+//   producer warp   : stages the tile's 130 rows of 160 samples in shared memory, one bulk-TMA copy
+//                     (cp.async.bulk -> mbarrier) per row at pitch 164 words; rows that touch a clip edge
+//                     (reflect padding, zero tail, `lengths`) or are not 16-byte aligned are written by hand;
+//   4 + 4 fold warps: one thread per frame (= TMEM lane).  The E warps compute ee / eo, the O warps oe / oo
+//                     (window multiply and both folds fused: 5 flops per two values), split every value
+//                     into fp16 hi + lo and write the packed pairs straight into TENSOR MEMORY as the
+//                     A operand (tcgen05.st) - the data never touch shared memory again;
+//   MMA warp        : one elected thread issues, per unit, 6 K-steps x 3 passes + 2 leftover steps of
+//                     tcgen05.mma.kind::f16 (M 128, N 104, K 16; A from TMEM, B = the constant matrix from
+//                     shared memory, fp32 accumulator in TMEM): hi Bh + lo Bh + hi Bl, then
+//                     tcgen05.commit -> mbarrier hands the accumulator to the epilogue;
+//   4 + 4 epilogue  : two warps per TMEM lane quadrant pull their half of the 104 accumulator columns
+//     warps           into registers at once (tcgen05.ld), release the accumulator, and add w d^2 to the mels
+//                     of each bin - mel structure and weights are compile-time constants (FFMA immediates),
+//                     partial sums in registers; after the 4th unit: log10(max(., 1e-10)), 128-byte
+//                     coalesced row stores and the utterance's max key (warp REDUX + one atomicMax).
+// Tensor memory is exactly full: 408 operand columns (4 units x [hi | lo], tc_core.cuh) + 104 accumulator.
+// The (max - 8, (x + 4) / 4) step runs as the shared pass-2 kernel.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "kernels.h"
 #include "tc_core.cuh"
@@ -25,11 +32,10 @@ namespace b200mel {
 
 namespace {
 
-constexpr int kTcWorkerWarps = 8;
-constexpr int kTcWorkers = kTcWorkerWarps * 32;   // 256
-constexpr int kTcThreads = kTcWorkers + 32;       // + the MMA warp
-constexpr int kTcTmemCols = 512;
-constexpr int kTcStripBytes = kTcN * 16;          // one 8-half K strip of a 64-row operand
+constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpProducer = 17;
+constexpr int kTcWarps = 20;
+constexpr int kTcThreads = kTcWarps * 32;   // 640
+constexpr uint32_t kSpinLimit = 1u << 24;    // a protocol bug traps instead of hanging the device
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -39,24 +45,64 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+// ---- tensor memory stores / loads (32 lanes x 32 bit per column, this warp's lane quadrant) ----
+__device__ __forceinline__ void tmem_st1(uint32_t t, uint32_t a) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(t), "r"(a) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&d)[32]) {
+__device__ __forceinline__ void tmem_st2(uint32_t t, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t t, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t t, float* d) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(t) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t t, float* d) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(t) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t t, float* d) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(t) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t t, float* d) {
     uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -65,21 +111,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&d)[32]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        : "r"(t) : "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(r[i]);
 }
+// N columns starting at column address t, as 32 / 16 / 8 / 4-column pieces (N % 4 == 0); no wait
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t t, float* d) {
+    static_assert(N % 4 == 0 && N >= 0, "column count");
+    if constexpr (N >= 32) { tmem_ld32(t, d); tmem_ld_cols<N - 32>(t + 32, d + 32); }
+    else if constexpr (N >= 16) { tmem_ld16(t, d); tmem_ld_cols<N - 16>(t + 16, d + 16); }
+    else if constexpr (N >= 8) { tmem_ld8(t, d); tmem_ld_cols<N - 8>(t + 8, d + 8); }
+    else if constexpr (N >= 4) { tmem_ld4(t, d); tmem_ld_cols<N - 4>(t + 4, d + 4); }
+}
 
+// ---- tensor-core issue -------------------------------------------------------------------------
 // K-major, no-swizzle shared-memory operand descriptor (8 x 16 B core matrices):
-// start >> 4 | (K-direction core-matrix stride >> 4) << 16 | (row-group stride >> 4) << 32 | version 1 << 46
-__device__ __forceinline__ uint64_t operand_desc(uint32_t smem_addr) {
-    return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(kTcStripBytes >> 4) << 16) |
+// start >> 4 | (K-direction core-matrix stride >> 4) << 16 | (8-row group stride >> 4) << 32 | version 1 << 46
+__device__ __forceinline__ uint64_t operand_desc(uint32_t smem_addr, uint32_t k_stride_bytes) {
+    return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(k_stride_bytes >> 4) << 16) |
            (static_cast<uint64_t>(128 >> 4) << 32) | (1ull << 46);
 }
-// f16 x f16 -> f32, both operands K-major, N = 32, M = 128
-constexpr uint32_t kTcIdesc = (1u << 4) | (static_cast<uint32_t>(kTcDCols >> 3) << 17) | (static_cast<uint32_t>(kTcTileFrames >> 4) << 24);
+// f16 x f16 -> f32, both operands K-major, M = 128, N = 104
+constexpr uint32_t kTcIdesc = (1u << 4) | (static_cast<uint32_t>(kTcN >> 3) << 17) | (static_cast<uint32_t>(kTcTileFrames >> 4) << 24);
 
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
@@ -93,211 +147,296 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-struct TcSmem {
-    int audio, s_tile, b_main, b_corr, tap, win, tw, total;
+// ---- shared memory carve-up ----------------------------------------------------------------------
+constexpr int kSmemOperands = 0;                                                  // 139776 B, 128-byte aligned
+constexpr int kSmemAudio = kTcOperandBytes;                                       // 130 rows x 656 B
+constexpr int kSmemStraddle = kSmemAudio + kTcAudioWords * 4;                     // [2 buffers][4 quadrants][3][32] floats
+constexpr int kSmemBytes = kSmemStraddle + 2 * 4 * 3 * 32 * 4;
+static_assert(kSmemAudio % 128 == 0 && kSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct TcBarriers {
+    uint64_t audio_full, audio_empty;
+    uint64_t a_full[2], a_empty[2];   // [E sweep, O sweep]
+    uint64_t d_full, d_empty;
 };
-__host__ __device__ constexpr int align128(int v) { return (v + 127) & ~127; }
-__host__ __device__ constexpr TcSmem tc_smem(int n_mels) {
-    TcSmem l{};
-    l.audio = 0;
-    l.s_tile = align128(kTcAudioFloats * 4);
-    l.b_main = l.s_tile + align128((n_mels + 2) * kTcTileFrames * 4);
-    l.b_corr = l.b_main + 2 * kTcBMainHalves * 2;
-    l.tap = l.b_corr + 2 * kTcBCorrHalves * 2;
-    l.win = l.tap + 2 * kTcUnits * 16 * static_cast<int>(sizeof(TcTap));
-    l.tw = l.win + kTcN2 * 16 * 4;
-    l.total = l.tw + kTcN2 * 8 * 8;
-    return l;
-}
 
 template <typename InT> __device__ __forceinline__ float sample_to_float(InT v);
 template <> __device__ __forceinline__ float sample_to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float sample_to_float<int16_t>(int16_t v) { return static_cast<float>(v) * (1.0f / 32768.0f); }
 
+struct TileCoord { int64_t clip; int t0; };
+__device__ __forceinline__ TileCoord tile_coord(int64_t tile, int tiles_per_clip) {
+    TileCoord c;
+    c.clip = tile / tiles_per_clip;
+    c.t0 = static_cast<int>(tile - c.clip * tiles_per_clip) * kTcTileFrames;
+    return c;
+}
+
+// ---- producer: one tile of audio into shared memory ----------------------------------------------
 template <typename InT>
-__global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelArgs a, const TcTables* __restrict__ tt) {
+__device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoord& tc, float* s_audio, uint64_t* full, int lane) {
+    const InT* __restrict__ row = static_cast<const InT*>(a.audio) + tc.clip * a.stride_b;
+    int64_t valid = a.n_samples;
+    if (a.lengths != nullptr) {
+        const int64_t len = a.lengths[tc.clip];
+        valid = len < 0 ? 0 : (len < valid ? len : valid);
+    }
+    const int64_t s0 = static_cast<int64_t>(tc.t0) * kHop - kHalfWin;
+    const bool aligned = sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
+    // rows [r_lo, r_hi) are whole, real, in-range samples: bulk copies.  The rest is written by hand.
+    int r_lo = 0, r_hi = 0;
+    if (aligned) {
+        r_lo = s0 >= 0 ? 0 : static_cast<int>((-s0 + kHop - 1) / kHop);
+        const int64_t room = valid - s0;   // samples available from the tile origin
+        r_hi = room <= 0 ? 0 : static_cast<int>(room / kHop < kTcAudioRows ? room / kHop : kTcAudioRows);
+        if (r_hi < r_lo) r_hi = r_lo;
+    }
+    for (int r = 0; r < kTcAudioRows; ++r) {
+        if (r >= r_lo && r < r_hi) continue;
+        for (int c = lane; c < kHop; c += 32) {
+            const int64_t pos = s0 + static_cast<int64_t>(r) * kHop + c;
+            float v = 0.f;
+            if (pos < a.total + kHalfWin) {
+                const int64_t idx = reflect_source_index(pos, a.total);
+                if (idx >= 0 && idx < valid) v = sample_to_float<InT>(__ldg(row + idx));
+            }
+            s_audio[r * kTcRowPitch + c] = v;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(full, static_cast<uint32_t>(r_hi - r_lo) * (kHop * 4));
+    __syncwarp();
+    for (int r = r_lo + lane; r < r_hi; r += 32)
+        bulk_copy_g2s(smem_u32(s_audio + r * kTcRowPitch), row + s0 + static_cast<int64_t>(r) * kHop, kHop * 4, full);
+}
+
+// ---- fold warps: one sweep of one tile, A operand -> tensor memory -----------------------------------
+template <int SWEEP, int J>
+__device__ __forceinline__ void sweep_chunk_store(const float* fr, uint32_t lane_addr) {
+    uint32_t hf[4], lf[4], hs[4], ls[4];
+    tc_sweep_chunk<SWEEP, J>(fr, hf, lf, hs, ls);
+    constexpr int u1 = SWEEP == 0 ? 0 : 2, u2 = u1 + 1;
+    if constexpr (J < 2 * kTcMainSteps) {   // slots 8J..8J+7 of the main blocks
+        tmem_st4(lane_addr + tc_hi_col(u1) + 4 * J, hf); tmem_st4(lane_addr + tc_lo_col(u1) + 4 * J, lf);
+        tmem_st4(lane_addr + tc_hi_col(u2) + 4 * J, hs); tmem_st4(lane_addr + tc_lo_col(u2) + 4 * J, ls);
+    } else {                                // slots 96..101: [hi x 3 | lo x 3] columns of the leftover area
+        const uint32_t b1 = lane_addr + tc_left_col(u1), b2 = lane_addr + tc_left_col(u2);
+        tmem_st2(b1, hf[0], hf[1]); tmem_st2(b1 + 2, hf[2], lf[0]); tmem_st2(b1 + 4, lf[1], lf[2]);
+        tmem_st2(b2, hs[0], hs[1]); tmem_st2(b2 + 2, hs[2], ls[0]); tmem_st2(b2 + 4, ls[1], ls[2]);
+    }
+}
+template <int SWEEP, int... J>
+__device__ __forceinline__ void sweep_store(const float* fr, uint32_t lane_addr, std::integer_sequence<int, J...>) {
+    (sweep_chunk_store<SWEEP, J>(fr, lane_addr), ...);
+}
+
+// ---- epilogue helpers -----------------------------------------------------------------------------
+template <int NM, int HALF>
+__device__ __forceinline__ void epilogue_unit(int unit, uint32_t d_addr, uint64_t* d_full, uint64_t* d_empty, uint32_t parity,
+                                              int lane, float (&acc)[TcEpilogueLayout<NM>::acc_size(HALF)]) {
+    using L = TcEpilogueLayout<NM>;
+    float d[L::cols(HALF)];
+    mbar_wait(d_full, parity);
+    tc_fence_after();
+    tmem_ld_cols<L::cols(HALF)>(d_addr + L::col0(HALF), d);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(d_empty);   // the accumulator is in registers: the next unit may overwrite it
+    switch (unit) {
+        case -1: acc[0] += d[0] + d[L::cols(HALF) - 1]; break;   // bring-up: loads only
+        case 0: tc_epilogue_unit<NM, 0, HALF>(d, acc); break;
+        case 1: tc_epilogue_unit<NM, 1, HALF>(d, acc); break;
+        case 2: tc_epilogue_unit<NM, 2, HALF>(d, acc); break;
+        default: tc_epilogue_unit<NM, 3, HALF>(d, acc); break;
+    }
+}
+
+template <int NM, int HALF>
+__device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, TcBarriers* bars, float* s_straddle,
+                                              uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
+    using L = TcEpilogueLayout<NM>;
+    constexpr int ACC = L::acc_size(HALF);
+    float acc[ACC];
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
+    const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol;
+    uint32_t d_parity = 0, buf = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(tile, tiles_per_clip);
+        // unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep)
+#pragma unroll 1
+        for (int u = 0; u < kTcUnits; ++u) {
+            epilogue_unit<NM, HALF>(debug_stage == 4 ? -1 : u, d_addr, &bars->d_full, &bars->d_empty, d_parity, lane, acc);
+            d_parity ^= 1u;
+        }
+        // join the mels that straddle the split: half 1 hands its partial sums to half 0
+        float* strad = s_straddle + ((buf * 4 + quad) * 3) * 32 + lane;
+        if constexpr (HALF == 1) {
+#pragma unroll
+            for (int j = 0; j < L::straddle; ++j) strad[j * 32] = acc[j];
+        }
+        if constexpr (L::straddle > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        if constexpr (HALF == 0) {
+#pragma unroll
+            for (int j = 0; j < L::straddle; ++j) acc[L::high_base + j] += strad[j * 32];
+        }
+        buf ^= 1u;
+        // log10 clamp, coalesced row stores (lane = frame), utterance max
+        const int f = quad * 32 + lane, t = tc.t0 + f;
+        const bool live = t < a.n_frames;
+        constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
+        float* out = a.out + (tc.clip * NM + m_begin) * static_cast<int64_t>(a.n_frames) + t;
+        float mx = __uint_as_float(0xff800000u);
+#pragma unroll
+        for (int m = m_begin; m < m_end; ++m) {
+            const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
+            if (live) { if (debug_stage != 5) *out = lg; mx = max_nan(mx, lg); }
+            out += a.n_frames;
+        }
+#pragma unroll
+        for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
+        uint32_t key = live ? max_key_encode(mx) : 0u;
+        key = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0 && debug_stage != 5) atomicMax(a.max_keys + (a.global_max ? 0 : tc.clip), key);
+    }
+}
+
+template <typename InT, int NM>
+__global__ void __launch_bounds__(kTcThreads, 1)
+logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __restrict__ operands, const int debug_stage) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TcSmem L = tc_smem(a.n_mels);
-    float* s_audio = reinterpret_cast<float*>(smem_raw + L.audio);
-    float* s_S = reinterpret_cast<float*>(smem_raw + L.s_tile);
-    __half* s_bmain = reinterpret_cast<__half*>(smem_raw + L.b_main);
-    __half* s_bcorr = reinterpret_cast<__half*>(smem_raw + L.b_corr);
-    TcTap (*s_tap)[kTcUnits][16] = reinterpret_cast<TcTap (*)[kTcUnits][16]>(smem_raw + L.tap);
-    float (*s_win)[16] = reinterpret_cast<float (*)[16]>(smem_raw + L.win);
-    float2 (*s_tw)[8] = reinterpret_cast<float2 (*)[8]>(smem_raw + L.tw);
-    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    float* s_audio = reinterpret_cast<float*>(smem_raw + kSmemAudio);
+    float* s_straddle = reinterpret_cast<float*>(smem_raw + kSmemStraddle);
+    __shared__ __align__(8) TcBarriers bars;
     __shared__ uint32_t s_tmem;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool worker = warp < kTcWorkerWarps;
-    const int quad = warp & 3, parity_role = (warp >> 2) & 1;   // workers: TMEM lane quadrant, even/odd half
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3;
     const int tiles_per_clip = (a.n_frames + kTcTileFrames - 1) / kTcTileFrames;
-    const int64_t total_tiles = a.batch * tiles_per_clip;
+    int64_t total_tiles = a.batch * tiles_per_clip;
+    // bring-up aid (B200MEL_TC_DEBUG): 1 = setup only, 2 = + producer and folds of ONE tile,
+    // 3 = + the tensor cores, 4 = + accumulator loads, 5 = + epilogue math, 6 = everything for one tile
+    if (debug_stage > 0 && debug_stage != 7 && total_tiles > gridDim.x) total_tiles = gridDim.x;
+    if (debug_stage == 1) total_tiles = 0;
 
-    // ---- one-time setup ----
+    // ---- one-time setup: tensor memory, barriers, constant matrices -> shared memory ----
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(static_cast<uint32_t>(kTcTmemCols)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
-        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-        mbar_init(&s_empty[0], kTcWorkers); mbar_init(&s_empty[1], kTcWorkers);
+    if (tid == 32) {
+        mbar_init(&bars.audio_full, 1);
+        mbar_init(&bars.audio_empty, 8);
+        mbar_init(&bars.a_full[0], 4); mbar_init(&bars.a_full[1], 4);
+        mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
+        mbar_init(&bars.d_full, 1);
+        mbar_init(&bars.d_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
-        const uint32_t* src_main = reinterpret_cast<const uint32_t*>(tt->b_main);
-        const uint32_t* src_corr = reinterpret_cast<const uint32_t*>(tt->b_corr);
-        uint32_t* dst_main = reinterpret_cast<uint32_t*>(s_bmain);
-        uint32_t* dst_corr = reinterpret_cast<uint32_t*>(s_bcorr);
-        for (int i = tid; i < kTcBMainHalves; i += kTcThreads) dst_main[i] = src_main[i];   // 2 sets x halves / 2 words
-        for (int i = tid; i < kTcBCorrHalves; i += kTcThreads) dst_corr[i] = src_corr[i];
-        const TcTap* src_tap = &tt->tap[0][0][0];
-        TcTap* dst_tap = &s_tap[0][0][0];
-        for (int i = tid; i < 2 * kTcUnits * 16; i += kTcThreads) dst_tap[i] = src_tap[i];
-        for (int i = tid; i < kTcN2 * 16; i += kTcThreads) (&s_win[0][0])[i] = (&tt->win[0][0])[i];
-        for (int i = tid; i < kTcN2 * 8; i += kTcThreads) (&s_tw[0][0])[i] = (&tt->tw[0][0])[i];
-        for (int i = tid; i < (a.n_mels + 2) * kTcTileFrames; i += kTcThreads) s_S[i] = 0.f;
+        const uint4* src = reinterpret_cast<const uint4*>(operands);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw + kSmemOperands);
+        for (int i = tid; i < kTcOperandBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand matrices: generic writes -> tensor-core reads
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async proxy) reads
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);   // this warp's TMEM lane quadrant
 
-    // zero every A column once: the 6 pad columns of each block are read (against zero B rows) and must stay finite
-    if (worker && parity_role == 0) {
-        for (int c = 0; c < kTcACols; ++c) tmem_st1(lane_addr + c, 0u);
+    if (warp < kWarpO) {
+        // zero every column once (every operand column is rewritten each tile; this only keeps idle lanes finite)
+        for (int c = 0; c < 512; c += 4) { const uint32_t z[4] = {0u, 0u, 0u, 0u}; tmem_st4(lane_addr + c, z); }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
-    uint32_t full_phase[2] = {0u, 0u}, empty_phase[2] = {0u, 0u};
-    const uint64_t desc_main0 = operand_desc(smem_u32(s_bmain));
-    const uint64_t desc_corr0 = operand_desc(smem_u32(s_bcorr));
-
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int64_t clip = tile / tiles_per_clip;
-        const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kTcTileFrames;
-
-        // ---- 1. stage the audio tile (reflect padding at the clip ends, zeros beyond `valid`) ----
-        {
-            const InT* __restrict__ row = static_cast<const InT*>(a.audio) + clip * a.stride_b;
-            int64_t valid = a.n_samples;
-            if (a.lengths != nullptr) {
-                const int64_t len = a.lengths[clip];
-                valid = len < 0 ? 0 : (len < valid ? len : valid);
-            }
-            const int64_t s0 = static_cast<int64_t>(t0) * kHop - kHalfWin;
-            if (sizeof(InT) == 4 && s0 >= 0 && s0 + kTcAudioSamples <= valid) {
-                // interior tile: asynchronous 4-byte copies, one 160-sample row per warp pass (rows land at pitch 161)
-                const InT* __restrict__ src = row + s0;
-                for (int r = warp; r < kTcAudioRows; r += kTcThreads / 32) {
-                    const int cols = r == kTcAudioRows - 1 ? kTcAudioSamples - kHop * (kTcAudioRows - 1) : kHop;
-                    const uint32_t dst = smem_u32(s_audio + r * kTcRowPitch);
-                    const InT* g = src + r * kHop;
-#pragma unroll
-                    for (int c = lane; c < kHop; c += 32)
-                        if (c < cols) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(g + c) : "memory");
-                }
-                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-            } else {
-                for (int r = warp; r < kTcAudioRows; r += kTcThreads / 32)
-                    for (int c = lane; c < kHop; c += 32) {
-                        const int i = r * kHop + c;
-                        float v = 0.f;
-                        if (i < kTcAudioSamples) {
-                            const int64_t pos = s0 + i;
-                            if (pos < a.total + kHalfWin) {
-                                const int64_t idx = reflect_source_index(pos, a.total);
-                                if (idx >= 0 && idx < valid) v = sample_to_float<InT>(__ldg(row + idx));
-                            }
-                        }
-                        s_audio[r * kTcRowPitch + c] = v;
-                    }
-            }
-        }
-        __syncthreads();
-
-        // ---- 2. stage 1 on the CUDA cores, A operand written to tensor memory ----
-        if (worker) {
-            const float* frame_audio = s_audio + kTcRowPitch * (quad * 32 + lane);
-            const int n2_begin = parity_role == 0 ? 0 : 13, n2_end = parity_role == 0 ? 13 : kTcN2;
-            for (int n2 = n2_begin; n2 < n2_end; ++n2) {
-                uint32_t hi[kTcBlocks], lo[kTcBlocks];
-                tc_stage1(frame_audio, n2, s_win[n2], s_tw[n2], hi, lo);
-#pragma unroll
-                for (int b = 0; b < kTcBlocks; ++b) {
-                    tmem_st1(lane_addr + kTcBlockCols * b + n2, hi[b]);
-                    tmem_st1(lane_addr + kTcBlockCols * b + kTcN2 + n2, lo[b]);
-                }
-            }
+    // register budget per warpgroup: the CTA is launched with 5 x 96; the warpgroups trade inside that total
+    // (a setmaxnreg.inc can only take what another warpgroup released): folds 80 + 80, epilogue 144 + 144, rest 32
+    if (warp < kWarpEpi0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        // ===== fold warps: E sweep (warps 0-3) / O sweep (warps 4-7) =====
+        const int sweep = warp < kWarpO ? 0 : 1;
+        const float* fr = s_audio + (quad * 32 + lane) * kTcRowPitch;
+        uint32_t parity = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&bars.audio_full, parity);
+            mbar_wait(&bars.a_empty[sweep], parity ^ 1u);   // the tensor cores are done with the previous tile's operand
+            tc_fence_after();
+            if (sweep == 0) sweep_store<0>(fr, lane_addr, std::make_integer_sequence<int, kTcChunks>{});
+            else sweep_store<1>(fr, lane_addr, std::make_integer_sequence<int, kTcChunks>{});
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bars.audio_empty); mbar_arrive(&bars.a_full[sweep]); }
+            parity ^= 1u;
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-
-        if (!worker) {
-            // ---- 3. stage 2 on the tensor cores: one elected thread issues, accumulators double buffered ----
-            for (int u = 0; u < kTcUnits; ++u) {
-                if (lane == 0) {
-                    const int buf = u & 1, b = u >> 1, h = u & 1;
-                    mbar_wait(&s_empty[buf], empty_phase[buf] ^ 1u);
-                    empty_phase[buf] ^= 1u;
+    } else if (warp < kWarpMma) {
+        // ===== epilogue warps =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+        if (debug_stage > 0 && debug_stage < 4) total_tiles = 0;
+        if (warp < kWarpEpi1) epilogue_role<NM, 0>(a, debug_stage, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        else epilogue_role<NM, 1>(a, debug_stage, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (warp == kWarpMma && lane == 0 && (debug_stage == 0 || debug_stage >= 3)) {
+            // ===== tensor-core issue: one elected thread =====
+            const uint32_t op_base = smem_u32(smem_raw + kSmemOperands);
+            const uint32_t d_tmem = tmem + kTcDCol;
+            uint32_t a_parity = 0, d_parity = 1;   // d_empty: the first wait passes (accumulator starts free)
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                // u is a compile-time constant on purpose: with a run-time u, nvcc 12.9 folded &bars.a_empty[u >> 1]
+                // into base + 4 u (right only for even u) and the commit hit a misaligned mbarrier
+#pragma unroll
+                for (int u = 0; u < kTcUnits; ++u) {
+                    if ((u & 1) == 0) { mbar_wait(&bars.a_full[u >> 1], a_parity); }
+                    if (u == 0 && debug_stage == 7) mbar_wait(&bars.a_full[1], a_parity);   // bring-up: no MMA while folds still store
+                    if (debug_stage != 3) mbar_wait(&bars.d_empty, d_parity);
+                    else if (u > 0) { mbar_wait(&bars.d_full, (u - 1) & 1); }
+                    d_parity ^= 1u;
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem + kTcDBase + kTcDCols * buf;
-                    const uint32_t a_tmem = tmem + kTcBlockCols * b;
-                    const uint32_t set_off = (b == 0 ? 0u : 1u);
-                    const uint64_t half_off = static_cast<uint64_t>((h * kTcDCols * 16) >> 4);
-                    const uint64_t dm = desc_main0 + ((set_off * kTcBMainHalves * 2) >> 4) + half_off;
-                    const uint64_t dc = desc_corr0 + ((set_off * kTcBCorrHalves * 2) >> 4) + half_off;
+                    const int m = tc_unit_matrix(u);
+                    const uint32_t a_hi = tmem + tc_hi_col(u), a_lo = tmem + tc_lo_col(u);
+                    const uint32_t b_hi = op_base + tc_matrix_offset(m, 0), b_lo = op_base + tc_matrix_offset(m, 1);
 #pragma unroll
-                    for (int s = 0; s < kTcKMain / 16; ++s)
-                        mma_f16_ts(d_tmem, a_tmem + 8 * s, dm + static_cast<uint64_t>((2 * kTcStripBytes * s) >> 4), s > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int s = 0; s < kTcKCorr / 16; ++s)
-                        mma_f16_ts(d_tmem, a_tmem + 8 * s, dc + static_cast<uint64_t>((2 * kTcStripBytes * s) >> 4), 1u);
-                    mma_commit(&s_full[buf]);
+                    for (int s = 0; s < kTcMainSteps; ++s) {   // K step s = strips 2s, 2s+1 = slots 16s..16s+15
+                        const uint64_t dh = operand_desc(b_hi + 2 * s * kTcStripBytes, kTcStripBytes);
+                        const uint64_t dl = operand_desc(b_lo + 2 * s * kTcStripBytes, kTcStripBytes);
+                        mma_f16_ts(d_tmem, a_hi + 8 * s, dh, s > 0 ? 1u : 0u);
+                        mma_f16_ts(d_tmem, a_lo + 8 * s, dh, 1u);
+                        mma_f16_ts(d_tmem, a_hi + 8 * s, dl, 1u);
+                    }
+                    // slots 96..101: one K step over the unit's [hi | lo] leftover columns, (hi + lo) Bh then hi Bl
+                    const uint32_t a_left = tmem + tc_left_start(u);
+                    mma_f16_ts(d_tmem, a_left, operand_desc(op_base + tc_left_offset(m, 0), kTcStripBytes), 1u);
+                    mma_f16_ts(d_tmem, a_left, operand_desc(op_base + tc_left_offset(m, 1), kTcStripBytes), 1u);
+                    mma_commit(&bars.d_full);
+                    if (u & 1) mma_commit(&bars.a_empty[u >> 1]);   // both units of the sweep have consumed its operand
                 }
-                __syncwarp();
+                a_parity ^= 1u;
             }
-        } else {
-            // ---- 4. epilogue: power of 16 bins per unit -> this thread's mel taps ----
-            char* s_col = reinterpret_cast<char*>(s_S + quad * 32 + lane);
-            for (int u = 0; u < kTcUnits; ++u) {
-                const int buf = u & 1;
-                mbar_wait(&s_full[buf], full_phase[buf]);
-                full_phase[buf] ^= 1u;
-                tc_fence_after();
-                float d[32];
-                tmem_ld32(lane_addr + kTcDBase + kTcDCols * buf, d);
-                tc_fence_before();
-                mbar_arrive(&s_empty[buf]);
-                tc_accumulate(d, s_tap[parity_role][u], s_col);
+            if (debug_stage == 3 && total_tiles > 0) mbar_wait(&bars.d_full, 1);   // nobody drains the accumulator in this stage
+        } else if (warp == kWarpProducer) {
+            // ===== audio producer =====
+            uint32_t parity = 1;   // audio_empty: the first wait passes
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&bars.audio_empty, parity);
+                parity ^= 1u;
+                produce_tile<InT>(a, tile_coord(tile, tiles_per_clip), s_audio, &bars.audio_full, lane);
             }
-            // ---- 5. log10 clamp, coalesced stores, max key; clear the S column for the next tile ----
-            const int f = quad * 32 + lane, t = t0 + f;
-            float mx = __uint_as_float(0xff800000u);
-            float* out = a.out + (clip * a.n_mels + parity_role) * static_cast<int64_t>(a.n_frames) + t;
-            for (int m = parity_role; m < a.n_mels; m += 2) {
-                const float lg = log10_clamped(s_S[m * kTcTileFrames + f]);
-                s_S[m * kTcTileFrames + f] = 0.f;
-                if (t < a.n_frames) { *out = lg; mx = max_nan(mx, lg); }
-                out += 2 * static_cast<int64_t>(a.n_frames);
-            }
-            uint32_t key = t < a.n_frames ? max_key_encode(mx) : 0u;
-            key = __reduce_max_sync(0xffffffffu, key);
-            if (lane == 0) atomicMax(a.max_keys + (a.global_max ? 0 : clip), key);
         }
-        tc_fence_before();
-        __syncthreads();   // every accumulator is drained: tensor memory and the audio tile are free again
-        tc_fence_after();
+        __syncwarp();
     }
 
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(static_cast<uint32_t>(kTcTmemCols)) : "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-template <typename InT>
+template <typename InT, int NM>
 cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t stream) {
     constexpr int kMaxDevices = 64;
     static int sms_by_device[kMaxDevices] = {0};
@@ -306,7 +445,7 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     if (err != cudaSuccess) return err;
     if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
     if (sms_by_device[device] == 0) {
-        err = cudaFuncSetAttribute(logmel_tc_kernel<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem(kMaxMels).total);
+        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (err != cudaSuccess) return err;
         int sms = 0;
         if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return err;
@@ -316,7 +455,8 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     const int64_t tiles = a.batch * tiles_per_clip;
     const unsigned grid = static_cast<unsigned>(tiles < sms_by_device[device] ? tiles : sms_by_device[device]);
     ProfileScope profile(2, stream);
-    logmel_tc_kernel<InT><<<grid, kTcThreads, tc_smem(a.n_mels).total, stream>>>(a, tables);
+    static const int debug_stage = std::getenv("B200MEL_TC_DEBUG") ? std::atoi(std::getenv("B200MEL_TC_DEBUG")) : 0;
+    logmel_tc_kernel<InT, NM><<<grid, kTcThreads, kSmemBytes, stream>>>(a, tables->operands, debug_stage);
     count_launch();
     return cudaGetLastError();
 }
@@ -326,7 +466,9 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
 cudaError_t launch_tc_pass1(const LogmelArgs& a, const TcTables* tables, int dtype, cudaStream_t stream) {
     const int tiles_per_clip = (a.n_frames + kTcTileFrames - 1) / kTcTileFrames;
     if (a.batch * tiles_per_clip <= 0) return cudaSuccess;
-    return dtype == 0 ? launch_tc<float>(a, tables, stream) : launch_tc<int16_t>(a, tables, stream);
+    if (a.n_mels == 80) return dtype == 0 ? launch_tc<float, 80>(a, tables, stream) : launch_tc<int16_t, 80>(a, tables, stream);
+    if (a.n_mels == 128) return dtype == 0 ? launch_tc<float, 128>(a, tables, stream) : launch_tc<int16_t, 128>(a, tables, stream);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace b200mel

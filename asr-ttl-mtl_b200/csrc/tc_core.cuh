@@ -1,157 +1,304 @@
-// Math core of the tcgen05 (tensor-core) variant of the log-mel front-end, shared by the sm_100a
-// kernel (logmel_tc.cu) and the CPU emulator (tests/emul/emul_tc.cpp).
+// Math core of the tcgen05 (tensor-core) variant of the log-mel front-end: the "folded DFT as GEMM".
+// Shared by the sm_100a kernel (logmel_tc.cu) and the CPU emulator (tests/emul/emul_tc.cpp), so the
+// index maps, the fp16 split and the epilogue can be checked without a GPU.
 //
-// The 400-point real DFT of a frame is factored 16 x 25 (n = 25 n1 + n2, k = k1 + 16 k2):
-//   stage 1, CUDA cores : Y[k1, n2] = sum_n1 w[25 n1 + n2] x[25 n1 + n2] W16^(n1 k1)      (real FFT-16, k1 = 0..8)
-//                         Yt[b, n2] = Y[b, n2] * W400^(n2 b)                                (twiddle, b = 1..7)
-//   stage 2, tcgen05    : X[b + 16 k2] = sum_n2 Yt[b, n2] W25^(n2 k2)                       (DFT-25 as a GEMM)
-// Stage 2 is a dense contraction whose matrix is THE SAME for b = 1..7 (the twiddles were applied
-// on the CUDA cores), so one 50 x 50 real matrix serves seven "blocks"; block 0 packs the two real
-// rows (Y[0, n2], Y[8, n2]) and has its own matrix (bins 16 k2 and 8 + 16 k2).
-// Precision: fp32 values are split x = hi + lo with hi, lo in fp16 (22 mantissa bits together) and
-// the product is formed as hi*Bhi + lo*Bhi + hi*Blo with fp32 accumulation in tensor memory — the
-// 3-product compensation of "3xTF32", at the f16 MMA rate and half the operand bytes.  Inputs are
-// pre-scaled by 2^8 (through the window table) so the lo parts stay normal fp16 numbers; the mel
-// weights carry the 2^-16 that undoes it (both exact).
+// Reference: whisper/audio.py:147-154 (Hann window, torch.stft, |.|^2, mel projection, log10).
+//
+// For one frame with samples x[0..399] and y[n] = hann[n] x[n] (hann[0] = 0, hann[400-n] = hann[n]):
+//   Re X[k] =  sum_{n=1}^{199} (y[n] + y[400-n]) cos(2 pi k n / 400) + (-1)^k y[200]
+//   Im X[k] = -sum_{n=1}^{199} (y[n] - y[400-n]) sin(2 pi k n / 400)
+// and a second fold n <-> 200-n separates even and odd bins, leaving FOUR real 100 x 100 products
+// ("units") instead of one 400 x 402 one:
+//   unit 0 (E sweep)  Re X[2k']    = sum_r ee[r] cos(2 pi k' r / 200)          ee[n] = e[n] + e[200-n]
+//   unit 1 (E sweep)  Re X[2k'+1]  = sum_r eo[r] cos(pi (2k'+1) r / 200)       eo[n] = e[n] - e[200-n]
+//   unit 2 (O sweep) -Im X[2k']    = sum_r oe[100-r] sin(2 pi k' (100-r) / 200) oe[n] = o[n] - o[200-n]
+//   unit 3 (O sweep) +-Im X[2k'+1] = sum_r oo[100-r] cos(pi (2k'+1) r / 200)   oo[n] = o[n] + o[200-n]
+// with e[n] = y[n] + y[400-n], o[n] = y[n] - y[400-n], r = 0..100 and k' = 0..99.  Units 1 and 3 share one
+// matrix (sin(pi (2k'+1) n / 200) = (-1)^k' cos(pi (2k'+1) (100-n) / 200); the sign dies in the square).
+// The centre terms need no special code: the uniform butterfly yields 2 y[200] at r = 0 and 2 e[100] /
+// 2 o[100] at the other centre, and the matrices carry a factor 1/2 on those rows (tc_tables.h).
+//
+// The folds (adds and the window multiply) run on the CUDA cores, one thread per frame; the four
+// products run on the tensor cores as D[128 frames, 104 bins] += A[128, 16] B[16, 104] with the data as
+// the A operand in TENSOR MEMORY.  Precision: every fp32 value v is split v = hi + lo with hi, lo fp16
+// (22 significant bits) and the constant matrices likewise B = Bh + Bl; the product is formed as
+// hi Bh + lo Bh + hi Bl with fp32 accumulation - the three-product compensation of "3xTF32", at the f16
+// MMA rate.  Data are pre-scaled by 2^8 (through the window constants) and the matrices by 2^4 so the lo
+// parts stay normal fp16 numbers; the mel weights carry the 2^-24 that undoes both (all exact).
 #pragma once
 
 #include <stdint.h>
 
+#include <utility>
+
 #include <cuda_fp16.h>
 
 #include "logmel_core.cuh"
+#include "mel_bands.h"
 
 namespace b200mel {
 
-constexpr int kTcTileFrames = 128;                    // frames per tile = TMEM lanes = MMA M
-constexpr int kTcRowPitch = kHop + 1;                 // audio tile rows of 160 samples stored at pitch 161
+// ---- tile geometry -----------------------------------------------------------------------------
+constexpr int kTcTileFrames = 128;                   // frames per tile = TMEM lanes = MMA M
+constexpr int kTcRowPitch = kHop + 4;                // audio rows of 160 samples at pitch 164 words:
+                                                     // frame-per-thread 128-bit loads are conflict free
 constexpr int kTcAudioSamples = kHop * kTcTileFrames + (kNFFT - kHop);          // 20720
 constexpr int kTcAudioRows = (kTcAudioSamples + kHop - 1) / kHop;               // 130
-constexpr int kTcAudioFloats = kTcAudioRows * kTcRowPitch;                      // 20930
-constexpr int kTcBlocks = 8;                          // block 0: (Y0, Y8) pairs; blocks 1..7: twiddled Y[b]
-constexpr int kTcN2 = 25;
-constexpr int kTcBlockCols = 56;                      // TMEM columns per block: 25 hi | 25 lo | 6 zero pad
-constexpr int kTcACols = kTcBlocks * kTcBlockCols;    // 448
-constexpr int kTcDCols = 32;                          // accumulator columns of one unit (16 complex outputs)
-constexpr int kTcDBase = kTcACols;                    // two accumulator buffers at columns 448 and 480
-constexpr int kTcUnits = kTcBlocks * 2;               // (block, N-half) units per tile
-constexpr int kTcKMain = 112;                         // K of the hi|lo pass: 50 + 50 (+12 zero rows) halves, 7 k-steps
-constexpr int kTcKCorr = 64;                          // K of the hi * Blo pass: 50 (+14 zero rows) halves, 4 k-steps
-constexpr int kTcN = 64;                              // N of a block: 50 real outputs padded to 2 x 32
-constexpr float kTcInputScale = 256.0f;               // exact power of two, see header
-constexpr float kTcPowerUnscale = 1.0f / 65536.0f;
+constexpr int kTcAudioWords = kTcAudioRows * kTcRowPitch;                       // 21320
+constexpr int kTcUnits = 4;
+constexpr int kTcN = 104;                            // MMA N: bins k' = 0..99 (+4 zero columns)
+constexpr int kTcBinsPerUnit = 100;
+constexpr int kTcMainSteps = 6;                      // K steps of 16 slots from the main blocks: slots r = 0..95
+constexpr int kTcLeftSlots = 6;                      // slots r = 96..101 (r = 101 is a zero) live in the leftover block
+constexpr int kTcChunks = 13;                        // 8 slots per sweep chunk (the 13th is the leftover)
+constexpr int kTcStripBytes = kTcN * 16;             // one 8-row K strip of a matrix (K-major, no swizzle)
+constexpr int kTcMainStrips = 2 * kTcMainSteps;      // strips of rows 0..95
+constexpr int kTcMatrixBytes = kTcMainStrips * kTcStripBytes;                   // 19968
+constexpr int kTcMatrices = 6;                       // {even-cos, odd-cos, even-sin} x {hi, lo}
+constexpr int kTcLeftStepBytes = 2 * kTcStripBytes;  // one 16-row operand of a leftover K step
+constexpr float kTcDataScale = 256.0f;               // 2^8, folded into the window constants
+constexpr float kTcMatrixScale = 16.0f;              // 2^4
+constexpr float kTcPowerUnscale = 1.0f / (65536.0f * 256.0f);                   // 2^-24
 
-// Operand matrices in the tcgen05 shared-memory layout (K-major, no swizzle: 8 x 16 B core matrices,
-// strips [k / 8][n][8 halves]).  Two sets: [0] block 0, [1] blocks 1..7.
-constexpr int kTcBMainHalves = kTcKMain * kTcN;       // 7168
-constexpr int kTcBCorrHalves = kTcKCorr * kTcN;       // 4096
+// which matrix (0 even-cos, 1 odd-cos, 2 even-sin) a unit multiplies with, and the parity of its bins
+B200_HD constexpr int tc_unit_matrix(int u) { return u == 0 ? 0 : (u == 2 ? 2 : 1); }
+B200_HD constexpr int tc_unit_bin(int u, int kp) { return (u == 0 || u == 2) ? 2 * kp : 2 * kp + 1; }
 
-// One output of a unit as seen by an epilogue thread: weight and byte offset (into the S tile row of
-// this thread) of the mel that this thread's parity owns at that bin; w == 0 when there is none.
-struct TcTap { float w; int s_off; };
+// ---- tensor-memory column map (512 columns, all used) --------------------------------------------
+// A column holds two fp16 slots (2c, 2c+1).  The A operand of tcgen05.mma must start at a column that is a
+// multiple of 4 (measured: profiles/microbench/tmem_align_test.cu), so:
+//   main blocks   unit u: hi slots 0..95 at columns [96u, 96u+48), lo slots 0..95 at [96u+48, 96u+96);
+//   leftover area columns [384, 408): unit u keeps hi slots 96..101 at 384+6u .. +2 and lo slots 96..101 at
+//                 384+6u+3 .. +5.  One extra K step per unit reads 8 columns from a multiple of 4 that covers
+//                 its 6 columns: units 0, 2 start AT their block (their slots are rows 0..11 of the step, the
+//                 neighbour's 2 columns meet zero rows), units 1, 3 start 2 columns EARLY (rows 4..15).
+//   accumulator   columns [408, 512).
+B200_HD constexpr int tc_hi_col(int u) { return 96 * u; }
+B200_HD constexpr int tc_lo_col(int u) { return 96 * u + 48; }
+B200_HD constexpr int tc_left_col(int u) { return 384 + 6 * u; }
+B200_HD constexpr int tc_left_pos(int u) { return u & 1; }                       // 0: rows 0..11, 1: rows 4..15
+B200_HD constexpr int tc_left_start(int u) { return tc_left_col(u) - 2 * tc_left_pos(u); }
+B200_HD constexpr int tc_matrix_left_pos(int matrix) { return matrix == 1 ? 1 : 0; }   // matrix 1 serves units 1 and 3
+constexpr int kTcDCol = 408;                         // accumulator: 104 columns
+static_assert(kTcDCol + kTcN == 512 && tc_left_col(3) + 6 == kTcDCol, "tensor memory is exactly full");
+static_assert(tc_left_start(0) % 4 == 0 && tc_left_start(1) % 4 == 0 && tc_left_start(2) % 4 == 0 && tc_left_start(3) % 4 == 0, "A operand alignment");
 
-struct TcTables {
-    float win[kTcN2][16];               // win[n2][n1] = 128 * hann[25 n1 + n2]  (FFT-16 below yields 2 X)
-    float2 tw[kTcN2][8];                // tw[n2][b] = W400^(n2 b), b = 1..7 ([0] unused)
-    __half b_main[2][kTcBMainHalves];   // [Bhi; Bhi; 0] in smem operand layout
-    __half b_corr[2][kTcBCorrHalves];   // [Blo; 0]
-    TcTap tap[2][kTcUnits][16];         // [mel parity][unit][complex output j]
-    int n_mels;
+// ---- Hann window, compile-time ------------------------------------------------------------------
+constexpr double tc_cos_poly(double x) {             // |x| <= pi/2, Taylor to 1e-17
+    const double x2 = x * x;
+    double term = 1.0, sum = 1.0;
+    for (int i = 1; i <= 14; ++i) { term *= -x2 / ((2.0 * i - 1.0) * (2.0 * i)); sum += term; }
+    return sum;
+}
+constexpr double tc_cos_2pi_n_over_400(int n) {      // n in [0, 200]
+    const double pi = 3.14159265358979323846;
+    return n <= 100 ? tc_cos_poly(pi * n / 200.0) : -tc_cos_poly(pi * (200 - n) / 200.0);
+}
+struct TcWindow { float v[201]; };
+constexpr TcWindow tc_make_window() {
+    TcWindow w{};
+    for (int n = 0; n <= 200; ++n) w.v[n] = static_cast<float>((0.5 - 0.5 * tc_cos_2pi_n_over_400(n)) * kTcDataScale);
+    return w;
+}
+constexpr TcWindow kTcWindow = tc_make_window();     // kTcWindow.v[n] = 256 hann[n]; hann[400-n] = hann[n]
+
+// ---- audio tile addressing ---------------------------------------------------------------------
+// word offset of sample n (0..399) of a frame whose first sample sits at the start of a row
+B200_HD constexpr int tc_off(int n) { return (n / kHop) * kTcRowPitch + n % kHop; }
+
+struct TcF4 { float v[4]; };
+B200_HD TcF4 tc_ld4(const float* fr, int n0) {       // samples n0..n0+3 (n0 % 4 == 0: one row, 16-byte aligned)
+    TcF4 r;
+#if defined(__CUDA_ARCH__)
+    const float4 q = *reinterpret_cast<const float4*>(fr + tc_off(n0));
+    r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+#else
+    for (int i = 0; i < 4; ++i) r.v[i] = fr[tc_off(n0 + i)];
+#endif
+    return r;
+}
+
+// ---- fp16 split ---------------------------------------------------------------------------------
+B200_HD uint32_t tc_half2_bits(__half2 h) {
+    union { __half2 h; uint32_t u; } c;
+    c.h = h;
+    return c.u;
+}
+// (v0, v1) -> packed hi pair and packed lo pair, v = hi + lo up to 2^-22 relative
+B200_HD void tc_split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    hi = tc_half2_bits(h);
+    lo = tc_half2_bits(__floats2half2_rn(v0 - hf.x, v1 - hf.y));
+}
+
+// ---- one sweep chunk: 8 slots of both units of a sweep ----------------------------------------------
+// SWEEP 0 (E): slot r = 8 J + i is n = r;        sa = x[n] + x[400-n], sb = x[200-n] + x[200+n]
+//              unit 0 gets ee = w[n] sa + w[200-n] sb, unit 1 gets eo = w[n] sa - w[200-n] sb.
+// SWEEP 1 (O): slot r = 8 J + i is n = 100 - r;  sa = x[n] - x[400-n], sb = x[200-n] - x[200+n]
+//              unit 2 gets oe = w[n] sa - w[200-n] sb, unit 3 gets oo = w[n] sa + w[200-n] sb.
+// Out-of-frame taps (x[400] at n = 0, n < 0) are never read; their slots are exact zeros.
+template <int SWEEP, int R>
+B200_HD void tc_point(float a, float b, float c, float d, float& plus, float& minus) {
+    constexpr int n = SWEEP == 0 ? R : 100 - R;
+    if constexpr (n < 0 || (SWEEP == 1 && n == 0)) {
+        plus = 0.f;
+        minus = 0.f;
+    } else {
+        constexpr float wa = kTcWindow.v[n], wb = kTcWindow.v[200 - n];
+        const float sa = SWEEP == 0 ? a + b : a - b;
+        const float sb = SWEEP == 0 ? c + d : c - d;
+        const float t = wa * sa;
+        plus = fmaf(wb, sb, t);
+        minus = fmaf(-wb, sb, t);
+    }
+}
+
+// Gathers the 4 x 8 taps of chunk J: a[i] = x[n], b[i] = x[400-n], c[i] = x[200-n], d[i] = x[200+n].
+template <int SWEEP, int J>
+B200_HD void tc_gather(const float* fr, float (&a)[8], float (&b)[8], float (&c)[8], float (&d)[8]) {
+    if constexpr (SWEEP == 0) {
+        constexpr int n0 = 8 * J;                                    // n = n0 + i ascending
+        const TcF4 a0 = tc_ld4(fr, n0), a1 = tc_ld4(fr, n0 + 4);
+        const TcF4 d0 = tc_ld4(fr, 200 + n0), d1 = tc_ld4(fr, 204 + n0);
+        const TcF4 b0 = tc_ld4(fr, 396 - n0), b1 = tc_ld4(fr, 392 - n0);   // x[399-n0 .. 393-n0] descending
+        const TcF4 c0 = tc_ld4(fr, 196 - n0), c1 = tc_ld4(fr, 192 - n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = a0.v[i]; a[4 + i] = a1.v[i]; d[i] = d0.v[i]; d[4 + i] = d1.v[i]; }
+        b[0] = n0 == 0 ? 0.f : fr[tc_off(n0 == 0 ? 0 : 400 - n0)];   // x[400] is outside the frame (weight 0)
+        c[0] = fr[tc_off(200 - n0)];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            b[i] = i <= 4 ? b0.v[4 - i] : b1.v[8 - i];
+            c[i] = i <= 4 ? c0.v[4 - i] : c1.v[8 - i];
+        }
+    } else {
+        constexpr int r0 = 8 * J;                                    // n = 100 - r0 - i descending
+        constexpr int last = (100 - r0 >= 8) ? 8 : (100 - r0 > 0 ? 100 - r0 : 0);   // slots with n >= 1
+        if constexpr (last == 8) {
+            const TcF4 b0 = tc_ld4(fr, 300 + r0), b1 = tc_ld4(fr, 304 + r0);   // x[400-n] ascending
+            const TcF4 c0 = tc_ld4(fr, 100 + r0), c1 = tc_ld4(fr, 104 + r0);   // x[200-n] ascending
+            const TcF4 a0 = tc_ld4(fr, 96 - r0), a1 = tc_ld4(fr, 92 - r0);     // x[n] descending from 99-r0
+            const TcF4 d0 = tc_ld4(fr, 296 - r0), d1 = tc_ld4(fr, 292 - r0);   // x[200+n] descending from 299-r0
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { b[i] = b0.v[i]; b[4 + i] = b1.v[i]; c[i] = c0.v[i]; c[4 + i] = c1.v[i]; }
+            a[0] = fr[tc_off(100 - r0)];
+            d[0] = fr[tc_off(300 - r0)];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) {
+                a[i] = i <= 4 ? a0.v[4 - i] : a1.v[8 - i];
+                d[i] = i <= 4 ? d0.v[4 - i] : d1.v[8 - i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool live = i < last;
+                a[i] = live ? fr[tc_off(live ? 100 - r0 - i : 0)] : 0.f;
+                b[i] = live ? fr[tc_off(live ? 300 + r0 + i : 0)] : 0.f;
+                c[i] = live ? fr[tc_off(live ? 100 + r0 + i : 0)] : 0.f;
+                d[i] = live ? fr[tc_off(live ? 300 - r0 - i : 0)] : 0.f;
+            }
+        }
+    }
+}
+
+// The chunk: packed hi/lo columns for the sweep's first unit (0 or 2) and second unit (1 or 3);
+// column c of the chunk holds slots 8 J + 2c, 8 J + 2c + 1.
+template <int SWEEP, int J>
+B200_HD void tc_sweep_chunk(const float* fr, uint32_t (&hi_first)[4], uint32_t (&lo_first)[4],
+                            uint32_t (&hi_second)[4], uint32_t (&lo_second)[4]) {
+    float a[8], b[8], c[8], d[8], first[8], second[8];
+    tc_gather<SWEEP, J>(fr, a, b, c, d);
+#define B200_TC_POINT(I)                                                              \
+    {                                                                                 \
+        float plus, minus;                                                            \
+        tc_point<SWEEP, 8 * J + I>(a[I], b[I], c[I], d[I], plus, minus);              \
+        first[I] = SWEEP == 0 ? plus : minus;                                         \
+        second[I] = SWEEP == 0 ? minus : plus;                                        \
+    }
+    B200_TC_POINT(0) B200_TC_POINT(1) B200_TC_POINT(2) B200_TC_POINT(3)
+    B200_TC_POINT(4) B200_TC_POINT(5) B200_TC_POINT(6) B200_TC_POINT(7)
+#undef B200_TC_POINT
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        tc_split_pack(first[2 * q], first[2 * q + 1], hi_first[q], lo_first[q]);
+        tc_split_pack(second[2 * q], second[2 * q + 1], hi_second[q], lo_second[q]);
+    }
+}
+
+// ---- epilogue: mel structure and weights are compile-time constants (mel_bands.h) ---------------------
+// Each bin feeds at most two neighbouring mels.  An epilogue thread owns one frame and one HALF of
+// every unit's columns (k' < split or k' >= split, i.e. bins below / above 2 split) and keeps the mels
+// its bins touch in registers; the (at most 3) mels that straddle the split are joined at the end.
+template <int NM> B200_HD constexpr int tc_bin_mel0(int k) { return MelBands<NM>::bin_mel0[k]; }
+template <int NM> B200_HD constexpr int tc_bin_count(int k) { return MelBands<NM>::bin_count[k]; }
+template <int NM> B200_HD constexpr bool tc_bands_supported() {   // the per-bin view agrees with the band edges
+    for (int k = 0; k < kUsedBins; ++k) {
+        int c = 0, m0 = -1;
+        for (int m = 0; m < NM; ++m)
+            if (MelBands<NM>::first[m] <= k && k <= MelBands<NM>::last[m]) { if (c == 0) m0 = m; ++c; }
+        if (c > 2 || c != MelBands<NM>::bin_count[k] || m0 != MelBands<NM>::bin_mel0[k]) return false;
+    }
+    return true;
+}
+
+template <int NM> B200_HD constexpr int tc_last_low_mel(int split_bin) {    // last mel with a bin below the split
+    int m = -1;
+    for (int i = 0; i < NM; ++i)
+        if (MelBands<NM>::first[i] < split_bin) m = i;
+    return m;
+}
+template <int NM> B200_HD constexpr int tc_first_high_mel(int split_bin) {  // first mel with a bin at or above it
+    for (int i = 0; i < NM; ++i)
+        if (MelBands<NM>::last[i] >= split_bin) return i;
+    return NM;
+}
+
+template <int NM> struct TcEpilogueLayout {
+    static constexpr int split = NM == 80 ? 44 : 40;      // columns [0, split) -> half 0, [split, 104) -> half 1
+    static constexpr int split_bin = 2 * split;           // half 0: bins < split_bin
+    static constexpr int low_mels = tc_last_low_mel<NM>(split_bin) + 1;    // half 0 accumulates mels [0, low_mels)
+    static constexpr int high_base = tc_first_high_mel<NM>(split_bin);     // half 1 accumulates mels [high_base, NM)
+    static constexpr int high_mels = NM - high_base;
+    static constexpr int straddle = low_mels - high_base;                  // mels both halves touch
+    static constexpr int cols(int half) { return half == 0 ? split : kTcN - split; }
+    static constexpr int col0(int half) { return half == 0 ? 0 : split; }
+    static constexpr int acc_size(int half) { return half == 0 ? low_mels : high_mels; }
+    static constexpr int acc_base(int half) { return half == 0 ? 0 : high_base; }
+    static_assert(tc_bands_supported<NM>(), "every bin must feed at most two neighbouring mels");
+    static_assert(straddle >= 0 && straddle <= 3, "unexpected mel layout around the split");
 };
 
-// ---- real FFT-16, returns 2 * X[k] for k = 0..8 (X[0], X[8] real) ---------------------------------
-// x[n1] are the 16 windowed samples.  Packed as z[m] = x[2m] + i x[2m+1], an 8-point complex FFT
-// (radix-2, decimation in time) and the usual real-FFT split.
-B200_HD void fft16_real_x2(const float (&x)[16], float2 (&X)[9]) {
-    const float r = 0.70710678118654752f;
-    float2 z[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) z[m] = make_float2(x[2 * m], x[2 * m + 1]);
-    // 8-point FFT: bit-reversed pairing (0,4)(2,6)(1,5)(3,7)
-    const float2 a0 = cadd(z[0], z[4]), a1 = csub(z[0], z[4]);
-    const float2 a2 = cadd(z[2], z[6]), a3 = csub(z[2], z[6]);
-    const float2 a4 = cadd(z[1], z[5]), a5 = csub(z[1], z[5]);
-    const float2 a6 = cadd(z[3], z[7]), a7 = csub(z[3], z[7]);
-    // 4-point combines: (a0,a1,a2,a3) -> even-index FFT4 E[0..3]; (a4..a7) -> odd-index FFT4 O[0..3]
-    const float2 e0 = cadd(a0, a2), e2 = csub(a0, a2);
-    const float2 e1 = make_float2(a1.x + a3.y, a1.y - a3.x);   // a1 - i a3
-    const float2 e3 = make_float2(a1.x - a3.y, a1.y + a3.x);   // a1 + i a3
-    const float2 o0 = cadd(a4, a6), o2 = csub(a4, a6);
-    const float2 o1 = make_float2(a5.x + a7.y, a5.y - a7.x);
-    const float2 o3 = make_float2(a5.x - a7.y, a5.y + a7.x);
-    // Z[k] = E[k] + W8^k O[k], Z[k+4] = E[k] - W8^k O[k];  W8 = (1 - i)/sqrt2, W8^2 = -i, W8^3 = (-1 - i)/sqrt2
-    const float2 t1 = make_float2(r * (o1.x + o1.y), r * (o1.y - o1.x));
-    const float2 t2 = make_float2(o2.y, -o2.x);
-    const float2 t3 = make_float2(r * (o3.y - o3.x), -r * (o3.x + o3.y));
-    float2 Z[8];
-    Z[0] = cadd(e0, o0); Z[4] = csub(e0, o0);
-    Z[1] = cadd(e1, t1); Z[5] = csub(e1, t1);
-    Z[2] = cadd(e2, t2); Z[6] = csub(e2, t2);
-    Z[3] = cadd(e3, t3); Z[7] = csub(e3, t3);
-    // real split: 2 X[k] = E'[k] + W16^k O'[k], 2 X[8-k] = conj(E'[k] - W16^k O'[k])
-    //   E'[k] = Z[k] + conj Z[8-k],  O'[k] = -i (Z[k] - conj Z[8-k])
-    X[0] = make_float2(2.0f * (Z[0].x + Z[0].y), 0.f);
-    X[8] = make_float2(2.0f * (Z[0].x - Z[0].y), 0.f);
-    X[4] = make_float2(2.0f * Z[4].x, -2.0f * Z[4].y);
-    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;   // cos, sin(pi/8)
-#pragma unroll
-    for (int k = 1; k <= 3; ++k) {
-        const float wr = k == 1 ? c1 : (k == 2 ? r : s1);    // W16^k = wr - i wi
-        const float wi = k == 1 ? s1 : (k == 2 ? r : c1);
-        const float2 zk = Z[k], zc = Z[8 - k];
-        const float2 E = make_float2(zk.x + zc.x, zk.y - zc.y);
-        const float2 O = make_float2(zk.y + zc.y, zc.x - zk.x);           // -i (zk - conj zc)
-        const float2 T = make_float2(O.x * wr + O.y * wi, O.y * wr - O.x * wi);   // O * (wr - i wi)
-        X[k] = make_float2(E.x + T.x, E.y + T.y);
-        X[8 - k] = make_float2(E.x - T.x, T.y - E.y);
+// one accumulator column: d = D[frame][k'] of unit U; adds w * d^2 to the (<= 2) mels of its bin
+template <int NM, int U, int HALF, int C, int ACC>
+B200_HD void tc_epilogue_col(float d, float (&acc)[ACC]) {
+    using L = TcEpilogueLayout<NM>;
+    constexpr int kp = L::col0(HALF) + C;
+    if constexpr (kp < kTcBinsPerUnit) {
+        constexpr int bin = tc_unit_bin(U, kp);
+        constexpr int cnt = tc_bin_count<NM>(bin);
+        if constexpr (cnt > 0) {
+            constexpr int m0 = tc_bin_mel0<NM>(bin) - L::acc_base(HALF);
+            static_assert(m0 >= 0 && m0 + cnt <= ACC, "bin outside the half's mel range");
+            constexpr float w0 = MelBands<NM>::bin_weight[bin][0] * kTcPowerUnscale;   // FFMA immediates
+            constexpr float w1 = MelBands<NM>::bin_weight[bin][1] * kTcPowerUnscale;
+            const float t = d * d;
+            acc[m0] = fmaf(w0, t, acc[m0]);
+            if constexpr (cnt == 2) acc[m0 + 1] = fmaf(w1, t, acc[m0 + 1]);
+        }
     }
 }
 
-// fp32 pair -> packed fp16 hi pair and packed fp16 lo pair (lo = x - float(hi), both round-to-nearest)
-B200_HD void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 back = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+template <int NM, int U, int HALF, int ACC, int NCOLS, int... C>
+B200_HD void tc_epilogue_cols(const float (&d)[NCOLS], float (&acc)[ACC], std::integer_sequence<int, C...>) {
+    (tc_epilogue_col<NM, U, HALF, C, ACC>(d[C], acc), ...);
 }
 
-// Stage 1 for one (frame, n2): 16 strided samples -> the 8 packed hi words and 8 packed lo words that
-// go to TMEM columns (56 b + n2) and (56 b + 25 + n2), b = 0..7.
-//   frame_audio: this frame's first sample inside the padded audio tile (row pitch 161)
-B200_HD void tc_stage1(const float* frame_audio, int n2, const float (&win)[16], const float2 (&tw)[8],
-                       uint32_t (&hi)[kTcBlocks], uint32_t (&lo)[kTcBlocks]) {
-    float x[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const int n = 25 * n1 + n2;
-        x[n1] = frame_audio[n + (n >= kHop) + (n >= 2 * kHop)] * win[n1];
-    }
-    float2 X[9];
-    fft16_real_x2(x, X);
-    split_pair(X[0].x, X[8].x, hi[0], lo[0]);
-#pragma unroll
-    for (int b = 1; b < kTcBlocks; ++b) {
-        const float2 t = cmul(X[b], tw[b]);
-        split_pair(t.x, t.y, hi[b], lo[b]);
-    }
-}
-
-// Epilogue of one unit for one thread: 16 complex outputs -> power -> accumulate this thread's
-// parity taps into its column of the S tile (s_col points at S[0][frame]).  The 16 taps of a unit
-// never alias (tc_tables.h), so all loads are issued before the stores.
-B200_HD void tc_accumulate(const float (&d)[32], const TcTap* taps, char* s_col) {
-    float acc[16];
-    int off[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const TcTap t = taps[j];
-        off[j] = t.s_off;
-        const float p = d[2 * j] * d[2 * j] + d[2 * j + 1] * d[2 * j + 1];
-        acc[j] = *reinterpret_cast<const float*>(s_col + t.s_off) + t.w * p;
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(s_col + off[j]) = acc[j];
+// all columns of one half of unit U (d[c] = accumulator column col0(HALF) + c)
+template <int NM, int U, int HALF, int ACC, int NCOLS>
+B200_HD void tc_epilogue_unit(const float (&d)[NCOLS], float (&acc)[ACC]) {
+    static_assert(NCOLS == TcEpilogueLayout<NM>::cols(HALF) && ACC == TcEpilogueLayout<NM>::acc_size(HALF), "half shape");
+    tc_epilogue_cols<NM, U, HALF, ACC, NCOLS>(d, acc, std::make_integer_sequence<int, NCOLS>{});
 }
 
 }  // namespace b200mel

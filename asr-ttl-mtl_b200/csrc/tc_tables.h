@@ -1,107 +1,100 @@
-// Host-side construction of the tcgen05 variant's constant operands (tc_core.cuh: TcTables).
-// Plain C++ (+ cuda_fp16.h host conversions) so the CPU emulator builds it with g++ too.
+// Host-side construction of the tcgen05 variant's constant operands: the three folded-DFT matrices
+// (fp16 hi / lo parts, already in the tensor-core shared-memory operand layout) and the run-time mel
+// weights.  Plain C++ plus cuda_fp16.h, so the CPU emulator builds it with g++ as well.
 #pragma once
 
 #include <cmath>
 #include <cstring>
 
+#include "tables.h"
 #include "tc_core.cuh"
 
 namespace b200mel {
 
-// index of element (n, k) in a K-major, no-swizzle tcgen05 operand of kTcN rows: strips [k/8][n][8]
-inline int tc_operand_index(int n, int k) { return (k / 8) * (kTcN * 8) + n * 8 + (k % 8); }
+// byte offset of element (row r = K slot, column kp = bin index k') inside one matrix:
+// K-major, no swizzle - 8 x 16-byte core matrices, strips [r / 8][kp][r % 8] of fp16
+inline int tc_operand_offset(int r, int kp) { return (r / 8) * kTcStripBytes + kp * 16 + (r % 8) * 2; }
 
-// Output order of a block: N-half h, slot j (0..15).  Within one half no two bins share a mel (they are
-// 16 bins apart and no filter is that wide), so an epilogue thread can pipeline its 16 tap updates.
-//   block 0 : half 0 = X[16 (j+1)] (j < 12, from Y[0,.]);  half 1 = X[8 + 16 j] (j < 12, from Y[8,.])
-//   block b : half 0 = X[b + 16 j] (j < 13, bins <= 199);  half 1 = X[b + 16 (13 + j)] (j < 12), mirrored to 400 - k
-// Returns the DFT index k (0..399) or -1 for a padding slot.
-inline int tc_output_k(int b, int h, int j) {
-    if (b == 0) return j < 12 ? (h == 0 ? 16 * (j + 1) : 8 + 16 * j) : -1;
-    if (h == 0) return j < 13 ? b + 16 * j : -1;
-    return j < 12 ? b + 16 * (13 + j) : -1;
+// Operand blob, copied verbatim into shared memory by every CTA:
+//   [matrix 0 even-cos, 1 odd-cos, 2 even-sin][part 0 hi, 1 lo][12 strips]   rows (slots) 0..95
+//   [matrix][0 main, 1 correction][2 strips]                                 the leftover K step (slots 96..101):
+//        main       rows = [zero x 4p | Bh[96..101] | Bh[96..101] | zero]  multiplies the step's [hi | lo] columns
+//        correction rows = [zero x 4p | Bl[96..101] | zero ...]            multiplies the same columns (hi Bl)
+//   with p = tc_matrix_left_pos(matrix).
+constexpr int kTcOperandBytes = kTcMatrices * kTcMatrixBytes + 3 * 2 * kTcLeftStepBytes;   // 139776
+struct TcTables {
+    unsigned char operands[kTcOperandBytes];
+    int n_mels;
+};
+B200_HD constexpr int tc_matrix_offset(int matrix, int part) { return (2 * matrix + part) * kTcMatrixBytes; }
+B200_HD constexpr int tc_left_offset(int matrix, int which) { return kTcMatrices * kTcMatrixBytes + (2 * matrix + which) * kTcLeftStepBytes; }
+
+// exact-phase cosine / sine of 2 pi p / 400 for an integer p
+inline double tc_cos400(long p) {
+    p %= 400; if (p < 0) p += 400;
+    if (p == 100 || p == 300) return 0.0;
+    return std::cos(6.283185307179586476925286766559 * static_cast<double>(p) / 400.0);
 }
-// bin (1..199) that slot feeds: |X[400-k]| = |X[k]| for real input
-inline int tc_output_bin(int b, int h, int j) {
-    const int k = tc_output_k(b, h, j);
-    return k < 0 ? -1 : (k <= 199 ? k : kNFFT - k);
+inline double tc_sin400(long p) {
+    p %= 400; if (p < 0) p += 400;
+    if (p == 0 || p == 200) return 0.0;
+    return std::sin(6.283185307179586476925286766559 * static_cast<double>(p) / 400.0);
 }
 
-// filters: float32 [n_mels, 201] row-major.  Returns kTablesOk or kTablesBadFilters.
-inline int build_tc_tables(int n_mels, const float* filters, TcTables* t) {
-    std::memset(static_cast<void*>(t), 0, sizeof(*t));
-    const double two_pi = 6.283185307179586476925286766559;
-    t->n_mels = n_mels;
-    for (int n2 = 0; n2 < kTcN2; ++n2) {
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const int n = 25 * n1 + n2;
-            t->win[n2][n1] = static_cast<float>(0.5 * kTcInputScale * (0.5 - 0.5 * std::cos(two_pi * n / kNFFT)));
-        }
-        for (int b = 0; b < 8; ++b) {
-            const double ang = -two_pi * n2 * b / kNFFT;
-            t->tw[n2][b] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
-        }
+// value of matrix `matrix` at (slot r, bin index kp), before the 2^4 scale (see tc_core.cuh header)
+inline double tc_matrix_value(int matrix, int r, int kp) {
+    if (r > 100 || kp >= kTcBinsPerUnit) return 0.0;
+    switch (matrix) {
+        case 0:  // Re X[2kp]: slot r is n = r; the centres r = 0 (2 y[200]) and r = 100 (2 e[100]) count half
+            return tc_cos400(2L * kp * r) * ((r == 0 || r == 100) ? 0.5 : 1.0);
+        case 1:  // Re X[2kp+1] (n = r) and Im X[2kp+1] (n = 100 - r): the r = 0 centre counts half, r = 100 is cos(odd pi/2) = 0
+            return r == 100 ? 0.0 : tc_cos400(static_cast<long>(2 * kp + 1) * r) * (r == 0 ? 0.5 : 1.0);
+        default:  // -Im X[2kp]: slot r is n = 100 - r
+            return tc_sin400(2L * kp * (100 - r));
     }
-    // dense stage-2 matrices B[k = (n2, re|im)][n = 32 h + 2 j + (re|im)], float64.
-    // X[k] = sum_n2 In[n2] exp(-2 pi i n2 k / 400) * (twiddle already applied for blocks 1..7, so the
-    // remaining factor there is W25^(n2 k2) = exp(-2 pi i n2 (k - b) / 400)).
-    static double B[2][50][kTcN];
-    std::memset(B, 0, sizeof(B));
-    for (int n2 = 0; n2 < kTcN2; ++n2)
-        for (int h = 0; h < 2; ++h)
-            for (int j = 0; j < 16; ++j) {
-                const int col = 32 * h + 2 * j;
-                int k = tc_output_k(1, h, j);            // blocks 1..7 share one matrix: use b = 1, k2 = (k - 1) / 16
-                if (k >= 0) {
-                    const double th = two_pi * n2 * ((k - 1) / 16) / 25.0, cs = std::cos(th), sn = std::sin(th);
-                    B[1][2 * n2][col] = cs;      B[1][2 * n2 + 1][col] = sn;       // (a + i b)(cos - i sin)
-                    B[1][2 * n2][col + 1] = -sn; B[1][2 * n2 + 1][col + 1] = cs;
-                }
-                k = tc_output_k(0, h, j);                // block 0: real inputs Y0 (row 2 n2) / Y8 (row 2 n2 + 1)
-                if (k >= 0) {
-                    const double th = two_pi * n2 * k / kNFFT;
-                    const int row = h == 0 ? 2 * n2 : 2 * n2 + 1;
-                    B[0][row][col] = std::cos(th);
-                    B[0][row][col + 1] = -std::sin(th);
-                }
+}
+
+// The epilogue's mel weights are compile-time constants (mel_bands.h): a plan can use the tcgen05 variant
+// only if its filter matrix is bit-equal to them.
+template <int NM>
+inline int tc_check_filters(const float* filters) {
+    for (int m = 0; m < NM; ++m)
+        for (int k = 0; k < kBins; ++k) {
+            float expect = 0.0f;
+            if (k < kUsedBins) {
+                const int j = m - MelBands<NM>::bin_mel0[k];
+                if (MelBands<NM>::bin_mel0[k] >= 0 && j >= 0 && j < MelBands<NM>::bin_count[k]) expect = MelBands<NM>::bin_weight[k][j];
             }
-    for (int set = 0; set < 2; ++set)
-        for (int n = 0; n < kTcN; ++n)
-            for (int k = 0; k < 50; ++k) {
-                const __half hi = __float2half_rn(static_cast<float>(B[set][k][n]));
-                const __half lo = __float2half_rn(static_cast<float>(B[set][k][n] - static_cast<double>(__half2float(hi))));
-                t->b_main[set][tc_operand_index(n, k)] = hi;       // rows 0..49  : Bhi (times A hi)
-                t->b_main[set][tc_operand_index(n, 50 + k)] = hi;  // rows 50..99 : Bhi (times A lo)
-                t->b_corr[set][tc_operand_index(n, k)] = lo;       // rows 0..49  : Blo (times A hi)
-            }
-    // epilogue taps
-    const int row_bytes = kTcTileFrames * static_cast<int>(sizeof(float));
-    for (int p = 0; p < 2; ++p)
-        for (int u = 0; u < kTcUnits; ++u)
-            for (int j = 0; j < 16; ++j) {
-                TcTap tap;
-                tap.w = 0.f;
-                tap.s_off = (n_mels + p) * row_bytes;  // scratch row of this parity
-                const int bin = tc_output_bin(u / 2, u % 2, j);
-                if (bin >= 0) {
-                    int found = 0;
-                    for (int m = p; m < n_mels; m += 2) {
-                        const float w = filters[static_cast<size_t>(m) * kBins + bin];
-                        if (w != 0.f) {
-                            if (found++) return kTablesBadFilters;  // two active mels of one parity at a bin
-                            tap.w = w * kTcPowerUnscale;
-                            tap.s_off = m * row_bytes;
-                        }
-                    }
-                }
-                t->tap[p][u][j] = tap;
-            }
-    // bins the variant never computes (0 and 200) must carry no weight
-    for (int m = 0; m < n_mels; ++m)
-        if (filters[static_cast<size_t>(m) * kBins] != 0.f || filters[static_cast<size_t>(m) * kBins + 200] != 0.f)
-            return kTablesBadFilters;
+            if (std::memcmp(&expect, filters + m * kBins + k, sizeof(float)) != 0 && !(expect == 0.0f && filters[m * kBins + k] == 0.0f))
+                return kTablesBadFilters;
+        }
     return kTablesOk;
+}
+
+// filters: float32 [n_mels, 201] row-major.  kTablesBadFilters: this is not the Whisper filterbank of
+// mel_bands.h, so only the FFT variant can serve the plan.
+inline int build_tc_tables(int n_mels, const float* filters, TcTables* t) {
+    std::memset(t, 0, sizeof(*t));
+    t->n_mels = n_mels;
+    for (int matrix = 0; matrix < 3; ++matrix)
+        for (int r = 0; r < 96 + kTcLeftSlots; ++r)
+            for (int kp = 0; kp < kTcN; ++kp) {
+                const double v = tc_matrix_value(matrix, r, kp) * kTcMatrixScale;
+                const __half hi = __float2half_rn(static_cast<float>(v));
+                const __half lo = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(hi))));
+                if (r < 96) {
+                    std::memcpy(t->operands + tc_matrix_offset(matrix, 0) + tc_operand_offset(r, kp), &hi, 2);
+                    std::memcpy(t->operands + tc_matrix_offset(matrix, 1) + tc_operand_offset(r, kp), &lo, 2);
+                } else {
+                    const int row = 4 * tc_matrix_left_pos(matrix) + (r - 96);   // row of the hi slot inside the leftover step
+                    std::memcpy(t->operands + tc_left_offset(matrix, 0) + tc_operand_offset(row, kp), &hi, 2);
+                    std::memcpy(t->operands + tc_left_offset(matrix, 0) + tc_operand_offset(row + kTcLeftSlots, kp), &hi, 2);
+                    std::memcpy(t->operands + tc_left_offset(matrix, 1) + tc_operand_offset(row, kp), &lo, 2);
+                }
+            }
+    if (n_mels == 80) return tc_check_filters<80>(filters);
+    if (n_mels == 128) return tc_check_filters<128>(filters);
+    return kTablesBadFilters;
 }
 
 }  // namespace b200mel

@@ -88,7 +88,7 @@ def emul_tc():
     src = os.path.join(EMUL_DIR, "emul_tc.cpp")
     lib = os.path.join(EMUL_DIR, "libemul_tc.so")
     csrc = os.path.join(ROOT, "asr-ttl-mtl_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("logmel_core.cuh", "tables.h", "tc_core.cuh", "tc_tables.h")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("logmel_core.cuh", "tables.h", "tc_core.cuh", "tc_tables.h", "mel_bands.h")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-Wno-strict-aliasing",
                         "-DB200_HOST_HAS_CUDA_HEADERS", "-I/usr/local/cuda/include", "-o", lib, src], check=True)
@@ -96,7 +96,9 @@ def emul_tc():
     fp = ctypes.POINTER(ctypes.c_float)
     h.emul_tc_logmel.argtypes = [fp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, fp, fp, ctypes.c_int]
     h.emul_tc_logmel.restype = ctypes.c_int
-    h.emul_fft16_real_x2.argtypes = [fp, fp]
+    dp = ctypes.POINTER(ctypes.c_double)
+    h.emul_tc_frame_spectrum.argtypes = [fp, dp, dp]
+    h.emul_tc_frame_spectrum.restype = ctypes.c_int
 
     def run(x, n_mels, filters, padding=0, valid=None, normalise=True):
         x = np.ascontiguousarray(x, dtype=np.float32)

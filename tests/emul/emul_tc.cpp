@@ -1,7 +1,7 @@
-// CPU emulator of the tcgen05 variant (TEST INFRASTRUCTURE, not a fallback): runs the stage-1 /
-// epilogue functions of csrc/tc_core.cuh with the kernel's tile geometry, tensor-memory column
-// layout and operand tables; the tensor-core MMAs are replaced by the exact fp16 x fp16 products
-// they stand for, read through the same operand layouts.
+// CPU emulator of the tcgen05 variant (TEST INFRASTRUCTURE, not a fallback): runs the sweep / epilogue
+// functions of csrc/tc_core.cuh with the kernel's tile geometry, tensor-memory column map and operand
+// tables (csrc/tc_tables.h); the tensor-core MMAs are replaced by the exact fp16 x fp16 products they stand
+// for, read through the same operand layouts - including the neighbour's columns a leftover K step reads.
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -12,26 +12,91 @@
 
 using namespace b200mel;
 
-static float half_at(const std::vector<uint32_t>& A, int frame, int half_index) {
-    const uint32_t word = A[frame * 512 + half_index / 2];
+namespace {
+
+float half_bits_to_float(uint16_t bits) {
     __half_raw raw;
-    raw.x = static_cast<unsigned short>((half_index & 1) ? (word >> 16) : (word & 0xffffu));
+    raw.x = bits;
     return __half2float(__half(raw));
 }
 
-extern "C" int emul_tc_logmel(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
-                              int n_mels, const float* filters, float* out, int do_normalise) {
+// fp16 element `slot` of a 7-step pass that starts at tensor-memory column `col0` of `frame`
+float a_at(const std::vector<uint32_t>& tmem, int frame, int col0, int slot) {
+    const uint32_t word = tmem[frame * 512 + col0 + slot / 2];
+    return half_bits_to_float(static_cast<uint16_t>((slot & 1) ? (word >> 16) : (word & 0xffffu)));
+}
+
+float b_bits(const TcTables& tab, int offset, int r, int kp) {
+    uint16_t bits;
+    std::memcpy(&bits, tab.operands + offset + tc_operand_offset(r, kp), 2);
+    return half_bits_to_float(bits);
+}
+
+// accumulator column kp of unit u for one frame: the 6 x 3 main MMAs and the 2 leftover MMAs, as issued
+float unit_column(const TcTables& tab, const std::vector<uint32_t>& tmem, int f, int u, int kp) {
+    const int m = tc_unit_matrix(u);
+    double acc = 0.0;
+    for (int r = 0; r < 16 * kTcMainSteps; ++r) {
+        const double bh = b_bits(tab, tc_matrix_offset(m, 0), r, kp), bl = b_bits(tab, tc_matrix_offset(m, 1), r, kp);
+        const double ah = a_at(tmem, f, tc_hi_col(u), r), al = a_at(tmem, f, tc_lo_col(u), r);
+        acc += ah * bh + al * bh + ah * bl;
+    }
+    for (int r = 0; r < 16; ++r) {   // the leftover K step reads 8 columns from tc_left_start(u)
+        const double av = a_at(tmem, f, tc_left_start(u), r);
+        acc += av * b_bits(tab, tc_left_offset(m, 0), r, kp) + av * b_bits(tab, tc_left_offset(m, 1), r, kp);
+    }
+    return static_cast<float>(acc);
+}
+
+template <int SWEEP, int J>
+void sweep_chunk_to_tmem(const float* fr, uint32_t* lane) {
+    uint32_t hf[4], lf[4], hs[4], ls[4];
+    tc_sweep_chunk<SWEEP, J>(fr, hf, lf, hs, ls);
+    constexpr int u1 = SWEEP == 0 ? 0 : 2, u2 = u1 + 1;
+    if (J < 12) {
+        for (int q = 0; q < 4; ++q) {
+            lane[tc_hi_col(u1) + 4 * J + q] = hf[q]; lane[tc_lo_col(u1) + 4 * J + q] = lf[q];
+            lane[tc_hi_col(u2) + 4 * J + q] = hs[q]; lane[tc_lo_col(u2) + 4 * J + q] = ls[q];
+        }
+    } else {
+        for (int q = 0; q < 3; ++q) {
+            lane[tc_left_col(u1) + q] = hf[q]; lane[tc_left_col(u1) + 3 + q] = lf[q];
+            lane[tc_left_col(u2) + q] = hs[q]; lane[tc_left_col(u2) + 3 + q] = ls[q];
+        }
+    }
+}
+
+template <int SWEEP, int... J>
+void sweep_to_tmem(const float* fr, uint32_t* lane, std::integer_sequence<int, J...>) {
+    (sweep_chunk_to_tmem<SWEEP, J>(fr, lane), ...);
+}
+
+template <int NM, int U>
+void epilogue_unit(const float* d, float* acc0, float* acc1) {
+    using L = TcEpilogueLayout<NM>;
+    float d0[L::cols(0)], d1[L::cols(1)];
+    float (&a0)[L::acc_size(0)] = *reinterpret_cast<float (*)[L::acc_size(0)]>(acc0);
+    float (&a1)[L::acc_size(1)] = *reinterpret_cast<float (*)[L::acc_size(1)]>(acc1);
+    for (int c = 0; c < L::cols(0); ++c) d0[c] = d[c];
+    for (int c = 0; c < L::cols(1); ++c) d1[c] = d[L::split + c];
+    tc_epilogue_unit<NM, U, 0>(d0, a0);
+    tc_epilogue_unit<NM, U, 1>(d1, a1);
+}
+
+template <int NM>
+int run(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad, const float* filters, float* out,
+        int do_normalise) {
+    using L = TcEpilogueLayout<NM>;
     static TcTables tab;
-    if (build_tc_tables(n_mels, filters, &tab) != kTablesOk) return 5;
+    if (build_tc_tables(NM, filters, &tab) != kTablesOk) return 5;
     const int64_t total = n_samples + (right_pad > 0 ? right_pad : 0);
     if (total <= kHalfWin) return 3;
     const int n_frames = static_cast<int>(total / kHop);
     const int tiles = (n_frames + kTcTileFrames - 1) / kTcTileFrames;
     if (valid > n_samples) valid = n_samples;
 
-    std::vector<float> s_audio(kTcAudioFloats);
-    std::vector<uint32_t> A(kTcTileFrames * 512, 0u);  // tensor memory: [lane][column]
-    std::vector<float> S((n_mels + 2) * kTcTileFrames, 0.f);
+    std::vector<float> s_audio(kTcAudioWords + 8, 0.f);
+    std::vector<uint32_t> tmem(kTcTileFrames * 512, 0u);   // tensor memory: [lane][column], zero-initialised like the kernel
     uint32_t clip_key = 0;
 
     for (int tile = 0; tile < tiles; ++tile) {
@@ -44,55 +109,73 @@ extern "C" int emul_tc_logmel(const float* audio, int64_t n_samples, int64_t val
                 const int64_t idx = reflect_source_index(s, total);
                 if (idx >= 0 && idx < valid) v = audio[idx];
             }
-            s_audio[i + i / kHop] = v;
+            s_audio[(i / kHop) * kTcRowPitch + i % kHop] = v;
         }
-        for (int f = 0; f < kTcTileFrames; ++f)
-            for (int n2 = 0; n2 < kTcN2; ++n2) {
-                uint32_t hi[kTcBlocks], lo[kTcBlocks];
-                tc_stage1(s_audio.data() + kTcRowPitch * f, n2, tab.win[n2], tab.tw[n2], hi, lo);
-                for (int b = 0; b < kTcBlocks; ++b) {
-                    A[f * 512 + kTcBlockCols * b + n2] = hi[b];
-                    A[f * 512 + kTcBlockCols * b + kTcN2 + n2] = lo[b];
+        for (int f = 0; f < kTcTileFrames; ++f) {
+            const float* fr = s_audio.data() + f * kTcRowPitch;
+            uint32_t* lane = tmem.data() + f * 512;
+            sweep_to_tmem<0>(fr, lane, std::make_integer_sequence<int, kTcChunks>{});
+            sweep_to_tmem<1>(fr, lane, std::make_integer_sequence<int, kTcChunks>{});
+        }
+        for (int f = 0; f < kTcTileFrames && t0 + f < n_frames; ++f) {
+            float acc0[L::acc_size(0)] = {0.f}, acc1[L::acc_size(1)] = {0.f};
+            for (int u = 0; u < kTcUnits; ++u) {
+                float d[kTcN];
+                for (int kp = 0; kp < kTcN; ++kp) d[kp] = unit_column(tab, tmem, f, u, kp);
+                switch (u) {
+                    case 0: epilogue_unit<NM, 0>(d, acc0, acc1); break;
+                    case 1: epilogue_unit<NM, 1>(d, acc0, acc1); break;
+                    case 2: epilogue_unit<NM, 2>(d, acc0, acc1); break;
+                    default: epilogue_unit<NM, 3>(d, acc0, acc1); break;
                 }
             }
-        for (int u = 0; u < kTcUnits; ++u) {
-            const int b = u / 2, h = u % 2, set = b == 0 ? 0 : 1;
-            for (int f = 0; f < kTcTileFrames; ++f) {
-                float d[32];
-                for (int n = 0; n < 32; ++n) {
-                    double acc = 0.0;
-                    for (int k = 0; k < kTcKMain; ++k)
-                        acc += static_cast<double>(half_at(A, f, 2 * kTcBlockCols * b + k)) *
-                               static_cast<double>(__half2float(tab.b_main[set][tc_operand_index(32 * h + n, k)]));
-                    for (int k = 0; k < kTcKCorr; ++k)
-                        acc += static_cast<double>(half_at(A, f, 2 * kTcBlockCols * b + k)) *
-                               static_cast<double>(__half2float(tab.b_corr[set][tc_operand_index(32 * h + n, k)]));
-                    d[n] = static_cast<float>(acc);
-                }
-                for (int p = 0; p < 2; ++p)
-                    tc_accumulate(d, tab.tap[p][u], reinterpret_cast<char*>(S.data() + f));
-            }
-        }
-        for (int f = 0; f < kTcTileFrames && t0 + f < n_frames; ++f)
-            for (int m = 0; m < n_mels; ++m) {
-                const float lg = log10_clamped(S[m * kTcTileFrames + f]);
+            for (int m = 0; m < NM; ++m) {
+                float s = 0.f;
+                if (m < L::low_mels) s += acc0[m];
+                if (m >= L::high_base) s += acc1[m - L::high_base];
+                const float lg = log10_clamped(s);
                 out[static_cast<int64_t>(m) * n_frames + t0 + f] = lg;
-                const uint32_t k = max_key_encode(lg);
-                if (k > clip_key) clip_key = k;
+                clip_key = std::max(clip_key, max_key_encode(lg));
             }
-        std::fill(S.begin(), S.end(), 0.f);
+        }
     }
     if (do_normalise) {
         const float g = max_key_decode(clip_key);
-        for (int64_t i = 0; i < static_cast<int64_t>(n_mels) * n_frames; ++i) out[i] = normalise(out[i], g);
+        for (int64_t i = 0; i < static_cast<int64_t>(NM) * n_frames; ++i) out[i] = normalise(out[i], g);
     }
     return 0;
 }
 
-extern "C" void emul_fft16_real_x2(const float* x16, float* out18) {
-    float x[16];
-    float2 X[9];
-    for (int i = 0; i < 16; ++i) x[i] = x16[i];
-    fft16_real_x2(x, X);
-    for (int k = 0; k < 9; ++k) { out18[2 * k] = X[k].x; out18[2 * k + 1] = X[k].y; }
+}  // namespace
+
+extern "C" int emul_tc_logmel(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
+                              int n_mels, const float* filters, float* out, int do_normalise) {
+    if (n_mels == 80) return run<80>(audio, n_samples, valid, right_pad, filters, out, do_normalise);
+    if (n_mels == 128) return run<128>(audio, n_samples, valid, right_pad, filters, out, do_normalise);
+    return 2;
+}
+
+// the folded spectrum of ONE frame (400 samples): out[2k], out[2k+1] = Re, |Im| partial products D / 4096
+// for bins k = 0..199, straight from the emulated accumulators (checks folds, matrices and slot maps)
+extern "C" int emul_tc_frame_spectrum(const float* frame400, double* re, double* im_abs) {
+    static TcTables tab;
+    static bool built = false;
+    if (!built) {
+        std::vector<float> dummy(80 * kBins, 0.f);
+        build_tc_tables(80, dummy.data(), &tab);   // the matrices do not depend on the filters (status ignored)
+        built = true;
+    }
+    std::vector<float> s_audio(3 * kTcRowPitch, 0.f);
+    for (int n = 0; n < kNFFT; ++n) s_audio[tc_off(n)] = frame400[n];
+    std::vector<uint32_t> tmem(512, 0u);
+    sweep_to_tmem<0>(s_audio.data(), tmem.data(), std::make_integer_sequence<int, kTcChunks>{});
+    sweep_to_tmem<1>(s_audio.data(), tmem.data(), std::make_integer_sequence<int, kTcChunks>{});
+    for (int u = 0; u < kTcUnits; ++u) {
+        for (int kp = 0; kp < kTcBinsPerUnit; ++kp) {
+            const int bin = tc_unit_bin(u, kp);
+            const double v = static_cast<double>(unit_column(tab, tmem, 0, u, kp)) / (kTcDataScale * kTcMatrixScale);
+            if (u < 2) re[bin] = v; else im_abs[bin] = v < 0 ? -v : v;
+        }
+    }
+    return 0;
 }

@@ -11,14 +11,30 @@ from oracle import signals
 TOL = 1e-4
 
 
-def test_real_fft16(emul_tc):
+def test_folded_dft_of_one_frame(emul_tc):
+    """Folds, slot maps and matrices: the four products give Re X[k] and |Im X[k]| of the Hann-windowed frame."""
     rng = np.random.default_rng(1)
-    fp = ctypes.POINTER(ctypes.c_float)
-    for _ in range(20):
-        x = rng.standard_normal(16).astype(np.float32)
-        out = np.zeros(18, np.float32)
-        emul_tc.emul_fft16_real_x2(x.ctypes.data_as(fp), out.ctypes.data_as(fp))
-        assert np.abs((out[0::2] + 1j * out[1::2]) - 2 * np.fft.rfft(x.astype(np.float64))).max() < 5e-6
+    fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    n = np.arange(400)
+    hann = 0.5 - 0.5 * np.cos(2 * np.pi * n / 400)
+    for trial in range(6):
+        x = rng.standard_normal(400).astype(np.float32)
+        if trial == 1:
+            x[:] = 0; x[200] = 1.0          # centre tap only
+        if trial == 2:
+            x[:] = 0; x[100] = 1.0; x[300] = -0.5
+        re, im = np.zeros(200), np.zeros(200)
+        assert emul_tc.emul_tc_frame_spectrum(x.ctypes.data_as(fp), re.ctypes.data_as(dp), im.ctypes.data_as(dp)) == 0
+        X = np.fft.rfft(hann * x.astype(np.float64))[:200]
+        scale = np.abs(X).max() + 1e-30
+        assert np.abs(re - X.real).max() / scale < 2e-6, trial
+        assert np.abs(im - np.abs(X.imag)).max() / scale < 2e-6, trial
+
+
+def test_mel_band_header_is_current():
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run([sys.executable, os.path.join(root, "tools", "gen_mel_bands.py"), "--check"]).returncode == 0
 
 
 def test_emulated_tc_variant_matches_golden_cases(emul_tc, golden):
