@@ -3,9 +3,9 @@
 // reference: whisper/audio.py:145-155).
 //
 // One persistent CTA per SM, warp-specialised, no __syncthreads in the steady state (mbarriers only):
-//   producer warp   : stages the tile's 130 rows of 160 samples in shared memory, one bulk-TMA copy
-//                     (cp.async.bulk -> mbarrier) per row at pitch 164 words; rows that touch a clip edge
-//                     (reflect padding, zero tail, `lengths`) or are not 16-byte aligned are written by hand;
+//   3 producer warps: stage the tile's 130 rows of 160 samples in shared memory at pitch 164 words with 16-byte
+//                     cp.async copies that complete on an mbarrier; chunks that touch a clip edge (reflect
+//                     padding, zero tail, `lengths`) or are not 16-byte aligned are written by hand;
 //   4 + 4 fold warps: one thread per frame (= TMEM lane).  The E warps compute ee / eo, the O warps oe / oo
 //                     (window multiply and both folds fused: 5 flops per two values), split every value
 //                     into fp16 hi + lo and write the packed pairs straight into TENSOR MEMORY as the
@@ -23,6 +23,7 @@
 // The (max - 8, (x + 4) / 4) step runs as the shared pass-2 kernel.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -32,10 +33,18 @@ namespace b200mel {
 
 namespace {
 
-constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpProducer = 17;
+constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpProducer = 17;   // producers: warps 17..19
 constexpr int kTcWarps = 20;
 constexpr int kTcThreads = kTcWarps * 32;   // 640
 constexpr uint32_t kSpinLimit = 1u << 24;    // a protocol bug traps instead of hanging the device
+
+// Bring-up timeline (B200MEL_TC_TRACE=1): CTA 0 stamps clock64() at the hand-over points of its first tiles.
+constexpr int kTraceTiles = 8, kTraceEvents = 16, kTraceRoles = 6;
+#define TC_TRACE(role, tile_index, event)                                                                        \
+    do {                                                                                                         \
+        if (trace != nullptr && blockIdx.x == 0 && (tile_index) < kTraceTiles && (threadIdx.x & 31) == 0)        \
+            trace[((role) * kTraceTiles + (tile_index)) * kTraceEvents + (event)] = clock64();                  \
+    } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -44,9 +53,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -61,10 +67,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (done) break;
         if (++spins > kSpinLimit) __trap();
     }
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -128,23 +130,52 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t t, float* d) {
 // ---- tensor-core issue -------------------------------------------------------------------------
 // K-major, no-swizzle shared-memory operand descriptor (8 x 16 B core matrices):
 // start >> 4 | (K-direction core-matrix stride >> 4) << 16 | (8-row group stride >> 4) << 32 | version 1 << 46
-__device__ __forceinline__ uint64_t operand_desc(uint32_t smem_addr, uint32_t k_stride_bytes) {
-    return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(k_stride_bytes >> 4) << 16) |
-           (static_cast<uint64_t>(128 >> 4) << 32) | (1ull << 46);
+// low word for the operand at shared address `smem_addr` (16-byte aligned, K strip stride = kTcStripBytes); operands
+// further along are reached by adding (byte offset >> 4) to it
+__device__ __forceinline__ uint32_t operand_desc_lo(uint32_t smem_addr) {
+    return ((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint32_t>(kTcStripBytes >> 4) << 16);
 }
 // f16 x f16 -> f32, both operands K-major, M = 128, N = 104
 constexpr uint32_t kTcIdesc = (1u << 4) | (static_cast<uint32_t>(kTcN >> 3) << 17) | (static_cast<uint32_t>(kTcTileFrames >> 4) << 24);
 
-__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kTcIdesc), "r"(accumulate) : "memory");
+// Issued by ONE elected lane of a converged warp (all operands warp-uniform): elect.sync inside the asm keeps the
+// compiler from wrapping every MMA in a per-thread serialisation loop.
+template <bool ACCUMULATE>
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo) {
+    const uint64_t b_desc = (static_cast<uint64_t>(0x4008u) << 32) | b_desc_lo;   // 8-row group stride 128 B, version 1
+    if constexpr (ACCUMULATE)
+        asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\n@P tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;\n}\n"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kTcIdesc) : "memory");
+    else
+        asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\n@P tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 0;\n}\n"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kTcIdesc) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\n@P tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
+// all tensor-core work of unit U for one tile: 6 K steps x (hi Bh, lo Bh, hi Bl) + the leftover step twice
+template <int U>
+__device__ __forceinline__ void mma_issue_unit(uint32_t tmem, uint32_t desc0) {
+    constexpr int m = tc_unit_matrix(U);
+    constexpr uint32_t kStep = (2 * kTcStripBytes) >> 4;   // K step s = strips 2s, 2s+1 = slots 16s..16s+15
+    const uint32_t d_tmem = tmem + kTcDCol;
+    const uint32_t a_hi = tmem + tc_hi_col(U), a_lo = tmem + tc_lo_col(U);
+    const uint32_t b_hi = desc0 + (tc_matrix_offset(m, 0) >> 4), b_lo = desc0 + (tc_matrix_offset(m, 1) >> 4);
+    mma_f16_ts<false>(d_tmem, a_hi, b_hi);
+    mma_f16_ts<true>(d_tmem, a_lo, b_hi);
+    mma_f16_ts<true>(d_tmem, a_hi, b_lo);
+#pragma unroll 1
+    for (uint32_t s = 1; s < kTcMainSteps; ++s) {
+        mma_f16_ts<true>(d_tmem, a_hi + 8 * s, b_hi + kStep * s);
+        mma_f16_ts<true>(d_tmem, a_lo + 8 * s, b_hi + kStep * s);
+        mma_f16_ts<true>(d_tmem, a_hi + 8 * s, b_lo + kStep * s);
+    }
+    // slots 96..101: one K step over the unit's [hi | lo] leftover columns, (hi + lo) Bh then hi Bl
+    const uint32_t a_left = tmem + tc_left_start(U);
+    mma_f16_ts<true>(d_tmem, a_left, desc0 + (tc_left_offset(m, 0) >> 4));
+    mma_f16_ts<true>(d_tmem, a_left, desc0 + (tc_left_offset(m, 1) >> 4));
 }
 
 // ---- shared memory carve-up ----------------------------------------------------------------------
@@ -172,9 +203,36 @@ __device__ __forceinline__ TileCoord tile_coord(int64_t tile, int tiles_per_clip
     return c;
 }
 
-// ---- producer: one tile of audio into shared memory ----------------------------------------------
+// ---- producers: one tile of audio into shared memory ---------------------------------------------
+// 96 threads (3 warps) move the tile as 5200 16-byte chunks (130 rows x 40) with cp.async (LDGSTS, L1
+// bypass): the source is one contiguous span, the destination rows sit at pitch 164 words.  A chunk that
+// touches a clip edge (reflect padding, zero tail, `lengths`), an unaligned row or int16 PCM is written by
+// hand.  Completion: every thread's copies arrive on `full` through cp.async.mbarrier.arrive.noinc, its
+// plain stores through a normal (release) arrive - the barrier expects 2 x 96 arrivals per tile.
+constexpr int kProducerThreads = 96;
+constexpr int kChunksPerRow = kHop / 4;                       // 40
+constexpr int kTileChunks = kTcAudioRows * kChunksPerRow;     // 5200
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+
+// Asks L2 for a later tile's samples (one bulk prefetch per tile, interior tiles only): the CTAs of a wave load in
+// lock-step, so without it every staging phase waits on an HBM burst while HBM idles the rest of the time.
 template <typename InT>
-__device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoord& tc, float* s_audio, uint64_t* full, int lane) {
+__device__ __forceinline__ void prefetch_tile_l2(const LogmelArgs& a, const TileCoord& tc) {
+    const InT* row = static_cast<const InT*>(a.audio) + tc.clip * a.stride_b;
+    const int64_t s0 = static_cast<int64_t>(tc.t0) * kHop - kHalfWin;
+    int64_t first = s0 < 0 ? 0 : s0, last = s0 + kTcAudioSamples;
+    if (last > a.n_samples) last = a.n_samples;
+    const uintptr_t begin = (reinterpret_cast<uintptr_t>(row + first) + 15u) & ~static_cast<uintptr_t>(15u);
+    const uintptr_t end = reinterpret_cast<uintptr_t>(row + last) & ~static_cast<uintptr_t>(15u);
+    if (end > begin)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(begin), "r"(static_cast<uint32_t>(end - begin)) : "memory");
+}
+
+template <typename InT>
+__device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoord& tc, float* s_audio, uint64_t* full, int pt) {
     const InT* __restrict__ row = static_cast<const InT*>(a.audio) + tc.clip * a.stride_b;
     int64_t valid = a.n_samples;
     if (a.lengths != nullptr) {
@@ -183,57 +241,75 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
     }
     const int64_t s0 = static_cast<int64_t>(tc.t0) * kHop - kHalfWin;
     const bool aligned = sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
-    // rows [r_lo, r_hi) are whole, real, in-range samples: bulk copies.  The rest is written by hand.
-    int r_lo = 0, r_hi = 0;
-    if (aligned) {
-        r_lo = s0 >= 0 ? 0 : static_cast<int>((-s0 + kHop - 1) / kHop);
-        const int64_t room = valid - s0;   // samples available from the tile origin
-        r_hi = room <= 0 ? 0 : static_cast<int>(room / kHop < kTcAudioRows ? room / kHop : kTcAudioRows);
-        if (r_hi < r_lo) r_hi = r_lo;
-    }
-    for (int r = 0; r < kTcAudioRows; ++r) {
-        if (r >= r_lo && r < r_hi) continue;
-        for (int c = lane; c < kHop; c += 32) {
-            const int64_t pos = s0 + static_cast<int64_t>(r) * kHop + c;
-            float v = 0.f;
-            if (pos < a.total + kHalfWin) {
-                const int64_t idx = reflect_source_index(pos, a.total);
-                if (idx >= 0 && idx < valid) v = sample_to_float<InT>(__ldg(row + idx));
+    const uint32_t dst0 = smem_u32(s_audio);
+    // chunk c = 40 r + k covers samples s0 + 4c .. + 3 and lands at word 164 r + 4 k
+    int r = pt / kChunksPerRow, k = pt - r * kChunksPerRow;   // pt < 96: r in {0, 1, 2}
+    if (aligned && s0 >= 0 && s0 + kTcAudioRows * kHop <= valid) {
+        const float* src = reinterpret_cast<const float*>(row) + s0 + 4 * pt;
+#pragma unroll 4
+        for (int c = pt; c < kTileChunks; c += kProducerThreads) {
+            cp_async16(dst0 + 4u * static_cast<uint32_t>(r * kTcRowPitch + 4 * k), src);
+            src += 4 * kProducerThreads;
+            r += 2; k += 16;                                   // 96 = 2 x 40 + 16
+            if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
+        }
+    } else {
+        for (int c = pt; c < kTileChunks; c += kProducerThreads) {
+            const int64_t pos = s0 + 4 * static_cast<int64_t>(c);
+            if (pos < s0 + kTcAudioSamples) {                  // the second half of row 129 is never read
+                float* dst = s_audio + r * kTcRowPitch + 4 * k;
+                if (aligned && pos >= 0 && pos + 4 <= valid) {
+                    cp_async16(smem_u32(dst), reinterpret_cast<const float*>(row) + pos);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float v = 0.f;
+                        if (pos + i < a.total + kHalfWin) {
+                            const int64_t idx = reflect_source_index(pos + i, a.total);
+                            if (idx >= 0 && idx < valid) v = sample_to_float<InT>(__ldg(row + idx));
+                        }
+                        dst[i] = v;
+                    }
+                }
             }
-            s_audio[r * kTcRowPitch + c] = v;
+            r += 2; k += 16;
+            if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
         }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive_expect_tx(full, static_cast<uint32_t>(r_hi - r_lo) * (kHop * 4));
-    __syncwarp();
-    for (int r = r_lo + lane; r < r_hi; r += 32)
-        bulk_copy_g2s(smem_u32(s_audio + r * kTcRowPitch), row + s0 + static_cast<int64_t>(r) * kHop, kHop * 4, full);
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full)) : "memory");
+    mbar_arrive(full);
 }
 
 // ---- fold warps: one sweep of one tile, A operand -> tensor memory -----------------------------------
-template <int SWEEP, int J>
-__device__ __forceinline__ void sweep_chunk_store(const float* fr, uint32_t lane_addr) {
+__constant__ TcFoldTable c_fold = tc_make_fold_table();
+
+// One compact loop serves both sweeps (the E and the O warps run the same instructions on different table rows
+// and tensor-memory columns), so the fold code stays resident in the instruction caches.
+__device__ __forceinline__ void sweep_store(int sweep, const float* fr, uint32_t lane_addr) {
+    const TcFoldChunk* __restrict__ table = c_fold.c[sweep];
+    const float sign = sweep == 0 ? 1.0f : -1.0f;
+    const uint32_t u1 = lane_addr + tc_hi_col(2) * sweep;          // hi block of the sweep's first unit (0 or 2)
     uint32_t hf[4], lf[4], hs[4], ls[4];
-    tc_sweep_chunk<SWEEP, J>(fr, hf, lf, hs, ls);
-    constexpr int u1 = SWEEP == 0 ? 0 : 2, u2 = u1 + 1;
-    if constexpr (J < 2 * kTcMainSteps) {   // slots 8J..8J+7 of the main blocks
-        tmem_st4(lane_addr + tc_hi_col(u1) + 4 * J, hf); tmem_st4(lane_addr + tc_lo_col(u1) + 4 * J, lf);
-        tmem_st4(lane_addr + tc_hi_col(u2) + 4 * J, hs); tmem_st4(lane_addr + tc_lo_col(u2) + 4 * J, ls);
-    } else {                                // slots 96..101: [hi x 3 | lo x 3] columns of the leftover area
-        const uint32_t b1 = lane_addr + tc_left_col(u1), b2 = lane_addr + tc_left_col(u2);
-        tmem_st2(b1, hf[0], hf[1]); tmem_st2(b1 + 2, hf[2], lf[0]); tmem_st2(b1 + 4, lf[1], lf[2]);
-        tmem_st2(b2, hs[0], hs[1]); tmem_st2(b2 + 2, hs[2], ls[0]); tmem_st2(b2 + 4, ls[1], ls[2]);
+#pragma unroll 1
+    for (int j = 0; j < 2 * kTcMainSteps; ++j) {                   // slots 8j..8j+7 of the main blocks
+        tc_sweep_chunk(fr, table[j], sign, hf, lf, hs, ls);
+        const uint32_t c = u1 + 4 * j;
+        tmem_st4(c, hf); tmem_st4(c + 48, lf);                     // unit: [hi 48 | lo 48], next unit 96 columns on
+        tmem_st4(c + 96, hs); tmem_st4(c + 144, ls);
     }
+    tc_sweep_chunk(fr, table[2 * kTcMainSteps], sign, hf, lf, hs, ls);
+    // slots 96..101: [hi x 3 | lo x 3] columns of the leftover area, second unit 6 columns on
+    const uint32_t b1 = lane_addr + tc_left_col(0) + (tc_left_col(2) - tc_left_col(0)) * sweep, b2 = b1 + 6;
+    tmem_st2(b1, hf[0], hf[1]); tmem_st2(b1 + 2, hf[2], lf[0]); tmem_st2(b1 + 4, lf[1], lf[2]);
+    tmem_st2(b2, hs[0], hs[1]); tmem_st2(b2 + 2, hs[2], ls[0]); tmem_st2(b2 + 4, ls[1], ls[2]);
 }
-template <int SWEEP, int... J>
-__device__ __forceinline__ void sweep_store(const float* fr, uint32_t lane_addr, std::integer_sequence<int, J...>) {
-    (sweep_chunk_store<SWEEP, J>(fr, lane_addr), ...);
-}
+static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) == 96 && tc_hi_col(3) - tc_hi_col(2) == 96 &&
+              tc_left_col(1) - tc_left_col(0) == 6 && tc_left_col(3) - tc_left_col(2) == 6, "column arithmetic of sweep_store");
 
 // ---- epilogue helpers -----------------------------------------------------------------------------
 template <int NM, int HALF>
 __device__ __forceinline__ void epilogue_unit(int unit, uint32_t d_addr, uint64_t* d_full, uint64_t* d_empty, uint32_t parity,
-                                              int lane, float (&acc)[TcEpilogueLayout<NM>::acc_size(HALF)]) {
+                                              int lane, float (&acc)[TcEpilogueLayout<NM>::acc_size(HALF)], long long* trace, int ti, int quad) {
     using L = TcEpilogueLayout<NM>;
     float d[L::cols(HALF)];
     mbar_wait(d_full, parity);
@@ -243,17 +319,17 @@ __device__ __forceinline__ void epilogue_unit(int unit, uint32_t d_addr, uint64_
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(d_empty);   // the accumulator is in registers: the next unit may overwrite it
+    if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * (unit < 0 ? 0 : unit) + 1);
     switch (unit) {
         case -1: acc[0] += d[0] + d[L::cols(HALF) - 1]; break;   // bring-up: loads only
-        case 0: tc_epilogue_unit<NM, 0, HALF>(d, acc); break;
-        case 1: tc_epilogue_unit<NM, 1, HALF>(d, acc); break;
-        case 2: tc_epilogue_unit<NM, 2, HALF>(d, acc); break;
-        default: tc_epilogue_unit<NM, 3, HALF>(d, acc); break;
+        // Re and Im of a bin take the same weights: units 0 / 2 (even bins) share one body, units 1 / 3 (odd bins) the other
+        case 0: case 2: tc_epilogue_unit<NM, 0, HALF>(d, acc); break;
+        default: tc_epilogue_unit<NM, 1, HALF>(d, acc); break;
     }
 }
 
 template <int NM, int HALF>
-__device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, TcBarriers* bars, float* s_straddle,
+__device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, long long* trace, TcBarriers* bars, float* s_straddle,
                                               uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
     using L = TcEpilogueLayout<NM>;
     constexpr int ACC = L::acc_size(HALF);
@@ -262,12 +338,15 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
     for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
     const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol;
     uint32_t d_parity = 0, buf = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int ti = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const TileCoord tc = tile_coord(tile, tiles_per_clip);
         // unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep)
 #pragma unroll 1
         for (int u = 0; u < kTcUnits; ++u) {
-            epilogue_unit<NM, HALF>(debug_stage == 4 ? -1 : u, d_addr, &bars->d_full, &bars->d_empty, d_parity, lane, acc);
+            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u);
+            epilogue_unit<NM, HALF>(debug_stage == 4 ? -1 : u, d_addr, &bars->d_full, &bars->d_empty, d_parity, lane, acc, trace, ti, quad);
+            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
             d_parity ^= 1u;
         }
         // join the mels that straddle the split: half 1 hands its partial sums to half 0
@@ -299,12 +378,14 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
         uint32_t key = live ? max_key_encode(mx) : 0u;
         key = __reduce_max_sync(0xffffffffu, key);
         if (lane == 0 && debug_stage != 5) atomicMax(a.max_keys + (a.global_max ? 0 : tc.clip), key);
+        if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
     }
 }
 
 template <typename InT, int NM>
 __global__ void __launch_bounds__(kTcThreads, 1)
-logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __restrict__ operands, const int debug_stage) {
+logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __restrict__ operands, const int debug_stage,
+                 long long* __restrict__ trace) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_audio = reinterpret_cast<float*>(smem_raw + kSmemAudio);
     float* s_straddle = reinterpret_cast<float*>(smem_raw + kSmemStraddle);
@@ -325,7 +406,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        mbar_init(&bars.audio_full, 1);
+        mbar_init(&bars.audio_full, 2 * kProducerThreads);
         mbar_init(&bars.audio_empty, 8);
         mbar_init(&bars.a_full[0], 4); mbar_init(&bars.a_full[1], 4);
         mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
@@ -362,70 +443,76 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
         const int sweep = warp < kWarpO ? 0 : 1;
         const float* fr = s_audio + (quad * 32 + lane) * kTcRowPitch;
         uint32_t parity = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int ti = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            if (quad == 0) TC_TRACE(1 + sweep, ti, 0);
             mbar_wait(&bars.audio_full, parity);
+            if (quad == 0) TC_TRACE(1 + sweep, ti, 1);
             mbar_wait(&bars.a_empty[sweep], parity ^ 1u);   // the tensor cores are done with the previous tile's operand
+            if (quad == 0) TC_TRACE(1 + sweep, ti, 2);
             tc_fence_after();
-            if (sweep == 0) sweep_store<0>(fr, lane_addr, std::make_integer_sequence<int, kTcChunks>{});
-            else sweep_store<1>(fr, lane_addr, std::make_integer_sequence<int, kTcChunks>{});
+            sweep_store(sweep, fr, lane_addr);
+            if (quad == 0) TC_TRACE(1 + sweep, ti, 3);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&bars.audio_empty); mbar_arrive(&bars.a_full[sweep]); }
+            if (quad == 0) TC_TRACE(1 + sweep, ti, 4);
             parity ^= 1u;
         }
     } else if (warp < kWarpMma) {
         // ===== epilogue warps =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         if (debug_stage > 0 && debug_stage < 4) total_tiles = 0;
-        if (warp < kWarpEpi1) epilogue_role<NM, 0>(a, debug_stage, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
-        else epilogue_role<NM, 1>(a, debug_stage, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        if (warp < kWarpEpi1) epilogue_role<NM, 0>(a, debug_stage, trace, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        else epilogue_role<NM, 1>(a, debug_stage, trace, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        if (warp == kWarpMma && lane == 0 && (debug_stage == 0 || debug_stage >= 3)) {
-            // ===== tensor-core issue: one elected thread =====
-            const uint32_t op_base = smem_u32(smem_raw + kSmemOperands);
-            const uint32_t d_tmem = tmem + kTcDCol;
+        if (warp == kWarpMma && (debug_stage == 0 || debug_stage >= 3)) {
+            // ===== tensor-core issue: the whole warp walks the loop, one elected lane issues =====
+            uint32_t desc0 = operand_desc_lo(smem_u32(smem_raw + kSmemOperands)), tmem_mma = tmem;
             uint32_t a_parity = 0, d_parity = 1;   // d_empty: the first wait passes (accumulator starts free)
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int ti = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
                 // u is a compile-time constant on purpose: with a run-time u, nvcc 12.9 folded &bars.a_empty[u >> 1]
                 // into base + 4 u (right only for even u) and the commit hit a misaligned mbarrier
 #pragma unroll
                 for (int u = 0; u < kTcUnits; ++u) {
                     if ((u & 1) == 0) { mbar_wait(&bars.a_full[u >> 1], a_parity); }
-                    if (u == 0 && debug_stage == 7) mbar_wait(&bars.a_full[1], a_parity);   // bring-up: no MMA while folds still store
+                    TC_TRACE(3, ti, 3 * u);
                     if (debug_stage != 3) mbar_wait(&bars.d_empty, d_parity);
                     else if (u > 0) { mbar_wait(&bars.d_full, (u - 1) & 1); }
                     d_parity ^= 1u;
+                    TC_TRACE(3, ti, 3 * u + 1);
                     tc_fence_after();
-                    const int m = tc_unit_matrix(u);
-                    const uint32_t a_hi = tmem + tc_hi_col(u), a_lo = tmem + tc_lo_col(u);
-                    const uint32_t b_hi = op_base + tc_matrix_offset(m, 0), b_lo = op_base + tc_matrix_offset(m, 1);
-#pragma unroll
-                    for (int s = 0; s < kTcMainSteps; ++s) {   // K step s = strips 2s, 2s+1 = slots 16s..16s+15
-                        const uint64_t dh = operand_desc(b_hi + 2 * s * kTcStripBytes, kTcStripBytes);
-                        const uint64_t dl = operand_desc(b_lo + 2 * s * kTcStripBytes, kTcStripBytes);
-                        mma_f16_ts(d_tmem, a_hi + 8 * s, dh, s > 0 ? 1u : 0u);
-                        mma_f16_ts(d_tmem, a_lo + 8 * s, dh, 1u);
-                        mma_f16_ts(d_tmem, a_hi + 8 * s, dl, 1u);
-                    }
-                    // slots 96..101: one K step over the unit's [hi | lo] leftover columns, (hi + lo) Bh then hi Bl
-                    const uint32_t a_left = tmem + tc_left_start(u);
-                    mma_f16_ts(d_tmem, a_left, operand_desc(op_base + tc_left_offset(m, 0), kTcStripBytes), 1u);
-                    mma_f16_ts(d_tmem, a_left, operand_desc(op_base + tc_left_offset(m, 1), kTcStripBytes), 1u);
+                    // keep the 80 descriptor / address constants out of registers: without this the compiler hoists every
+                    // base + constant out of the tile loop and spills them
+                    asm volatile("" : "+r"(desc0), "+r"(tmem_mma));
+                    if (u == 0) mma_issue_unit<0>(tmem_mma, desc0);
+                    else if (u == 1) mma_issue_unit<1>(tmem_mma, desc0);
+                    else if (u == 2) mma_issue_unit<2>(tmem_mma, desc0);
+                    else mma_issue_unit<3>(tmem_mma, desc0);
                     mma_commit(&bars.d_full);
+                    TC_TRACE(3, ti, 3 * u + 2);
                     if (u & 1) mma_commit(&bars.a_empty[u >> 1]);   // both units of the sweep have consumed its operand
                 }
                 a_parity ^= 1u;
             }
             if (debug_stage == 3 && total_tiles > 0) mbar_wait(&bars.d_full, 1);   // nobody drains the accumulator in this stage
-        } else if (warp == kWarpProducer) {
-            // ===== audio producer =====
+        } else if (warp >= kWarpProducer) {
+            // ===== audio producers =====
+            const int pt = tid - kWarpProducer * 32;
             uint32_t parity = 1;   // audio_empty: the first wait passes
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int ti = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                if (pt == 0) TC_TRACE(0, ti, 0);
+                // while waiting for the buffer, pull the NEXT tile towards L2 (the current one was prefetched a tile ago)
+                if (pt == 0 && tile + gridDim.x < total_tiles) prefetch_tile_l2<InT>(a, tile_coord(tile + gridDim.x, tiles_per_clip));
                 mbar_wait(&bars.audio_empty, parity);
+                if (pt == 0) TC_TRACE(0, ti, 1);
                 parity ^= 1u;
-                produce_tile<InT>(a, tile_coord(tile, tiles_per_clip), s_audio, &bars.audio_full, lane);
+                produce_tile<InT>(a, tile_coord(tile, tiles_per_clip), s_audio, &bars.audio_full, pt);
+                if (pt == 0) TC_TRACE(0, ti, 2);
             }
         }
         __syncwarp();
@@ -456,9 +543,32 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     const unsigned grid = static_cast<unsigned>(tiles < sms_by_device[device] ? tiles : sms_by_device[device]);
     ProfileScope profile(2, stream);
     static const int debug_stage = std::getenv("B200MEL_TC_DEBUG") ? std::atoi(std::getenv("B200MEL_TC_DEBUG")) : 0;
-    logmel_tc_kernel<InT, NM><<<grid, kTcThreads, kSmemBytes, stream>>>(a, tables->operands, debug_stage);
+    static long long* trace = nullptr;
+    static const bool want_trace = std::getenv("B200MEL_TC_TRACE") != nullptr;
+    constexpr size_t kTraceBytes = sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents;
+    if (want_trace && trace == nullptr) { cudaMalloc(&trace, kTraceBytes); }
+    if (want_trace) cudaMemsetAsync(trace, 0, kTraceBytes, stream);
+    logmel_tc_kernel<InT, NM><<<grid, kTcThreads, kSmemBytes, stream>>>(a, tables->operands, debug_stage, want_trace ? trace : nullptr);
     count_launch();
-    return cudaGetLastError();
+    err = cudaGetLastError();
+    if (want_trace && err == cudaSuccess) {   // bring-up only: synchronises and prints CTA 0's timeline
+        static long long host[kTraceRoles * kTraceTiles * kTraceEvents];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(host, trace, kTraceBytes, cudaMemcpyDeviceToHost);
+        long long t0 = 0;
+        for (long long v : host) if (v != 0 && (t0 == 0 || v < t0)) t0 = v;
+        static const char* names[kTraceRoles] = {"producer", "fold-E", "fold-O", "mma", "epi-0", "epi-1"};
+        for (int r = 0; r < kTraceRoles; ++r)
+            for (int t = 0; t < kTraceTiles; ++t) {
+                std::fprintf(stderr, "trace %-8s tile %d:", names[r], t);
+                for (int e = 0; e < kTraceEvents; ++e) {
+                    const long long v = host[(r * kTraceTiles + t) * kTraceEvents + e];
+                    if (v) std::fprintf(stderr, " %d:%lld", e, v - t0);
+                }
+                std::fprintf(stderr, "\n");
+            }
+    }
+    return err;
 }
 
 }  // namespace

@@ -132,93 +132,91 @@ B200_HD void tc_split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
     lo = tc_half2_bits(__floats2half2_rn(v0 - hf.x, v1 - hf.y));
 }
 
-// ---- one sweep chunk: 8 slots of both units of a sweep ----------------------------------------------
+// ---- one sweep chunk: 8 slots of both units of a sweep, table driven -----------------------------------
 // SWEEP 0 (E): slot r = 8 J + i is n = r;        sa = x[n] + x[400-n], sb = x[200-n] + x[200+n]
 //              unit 0 gets ee = w[n] sa + w[200-n] sb, unit 1 gets eo = w[n] sa - w[200-n] sb.
 // SWEEP 1 (O): slot r = 8 J + i is n = 100 - r;  sa = x[n] - x[400-n], sb = x[200-n] - x[200+n]
 //              unit 2 gets oe = w[n] sa - w[200-n] sb, unit 3 gets oo = w[n] sa + w[200-n] sb.
-// Out-of-frame taps (x[400] at n = 0, n < 0) are never read; their slots are exact zeros.
-template <int SWEEP, int R>
-B200_HD void tc_point(float a, float b, float c, float d, float& plus, float& minus) {
-    constexpr int n = SWEEP == 0 ? R : 100 - R;
-    if constexpr (n < 0 || (SWEEP == 1 && n == 0)) {
-        plus = 0.f;
-        minus = 0.f;
-    } else {
-        constexpr float wa = kTcWindow.v[n], wb = kTcWindow.v[200 - n];
-        const float sa = SWEEP == 0 ? a + b : a - b;
-        const float sb = SWEEP == 0 ? c + d : c - d;
-        const float t = wa * sa;
-        plus = fmaf(wb, sb, t);
-        minus = fmaf(-wb, sb, t);
-    }
-}
+// Both sweeps run the SAME code (one compact loop body instead of 26 unrolled chunks: the kernel is
+// instruction-fetch bound otherwise).  Per chunk a table entry gives the window weights and where the four
+// 8-tap runs sit in the audio tile: two ASCENDING runs (E: x[n], x[200+n]; O: x[400-n], x[200-n]) as two aligned
+// 4-sample groups each, and two DESCENDING runs (E: x[400-n], x[200-n]; O: x[n], x[200+n]) as one head sample plus
+// two aligned groups read backwards.  The O table carries -w[200-n], so "first = t + wb sb" is oe there.
+// Taps outside the frame (x[400] at n = 0; n < 0 in the O tail) get zero weights and an in-frame address.
+struct TcFoldChunk {
+    float wa[8], wb[8];      // 256 w[n], +-256 w[200-n] per slot (0 for slots without a tap)
+    int asc[2][2];           // byte offsets of the two aligned groups of each ascending run
+    int desc[2][2];          // byte offsets of the two aligned groups of each descending run (read backwards)
+    int head[2];             // byte offset of the first (highest) sample of each descending run
+    int pad[2];
+};
+struct TcFoldTable { TcFoldChunk c[2][kTcChunks]; };
 
-// Gathers the 4 x 8 taps of chunk J: a[i] = x[n], b[i] = x[400-n], c[i] = x[200-n], d[i] = x[200+n].
-template <int SWEEP, int J>
-B200_HD void tc_gather(const float* fr, float (&a)[8], float (&b)[8], float (&c)[8], float (&d)[8]) {
-    if constexpr (SWEEP == 0) {
-        constexpr int n0 = 8 * J;                                    // n = n0 + i ascending
-        const TcF4 a0 = tc_ld4(fr, n0), a1 = tc_ld4(fr, n0 + 4);
-        const TcF4 d0 = tc_ld4(fr, 200 + n0), d1 = tc_ld4(fr, 204 + n0);
-        const TcF4 b0 = tc_ld4(fr, 396 - n0), b1 = tc_ld4(fr, 392 - n0);   // x[399-n0 .. 393-n0] descending
-        const TcF4 c0 = tc_ld4(fr, 196 - n0), c1 = tc_ld4(fr, 192 - n0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = a0.v[i]; a[4 + i] = a1.v[i]; d[i] = d0.v[i]; d[4 + i] = d1.v[i]; }
-        b[0] = n0 == 0 ? 0.f : fr[tc_off(n0 == 0 ? 0 : 400 - n0)];   // x[400] is outside the frame (weight 0)
-        c[0] = fr[tc_off(200 - n0)];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) {
-            b[i] = i <= 4 ? b0.v[4 - i] : b1.v[8 - i];
-            c[i] = i <= 4 ? c0.v[4 - i] : c1.v[8 - i];
-        }
-    } else {
-        constexpr int r0 = 8 * J;                                    // n = 100 - r0 - i descending
-        constexpr int last = (100 - r0 >= 8) ? 8 : (100 - r0 > 0 ? 100 - r0 : 0);   // slots with n >= 1
-        if constexpr (last == 8) {
-            const TcF4 b0 = tc_ld4(fr, 300 + r0), b1 = tc_ld4(fr, 304 + r0);   // x[400-n] ascending
-            const TcF4 c0 = tc_ld4(fr, 100 + r0), c1 = tc_ld4(fr, 104 + r0);   // x[200-n] ascending
-            const TcF4 a0 = tc_ld4(fr, 96 - r0), a1 = tc_ld4(fr, 92 - r0);     // x[n] descending from 99-r0
-            const TcF4 d0 = tc_ld4(fr, 296 - r0), d1 = tc_ld4(fr, 292 - r0);   // x[200+n] descending from 299-r0
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { b[i] = b0.v[i]; b[4 + i] = b1.v[i]; c[i] = c0.v[i]; c[4 + i] = c1.v[i]; }
-            a[0] = fr[tc_off(100 - r0)];
-            d[0] = fr[tc_off(300 - r0)];
-#pragma unroll
-            for (int i = 1; i < 8; ++i) {
-                a[i] = i <= 4 ? a0.v[4 - i] : a1.v[8 - i];
-                d[i] = i <= 4 ? d0.v[4 - i] : d1.v[8 - i];
-            }
-        } else {
-#pragma unroll
+constexpr int tc_clamp_sample(int n) { return n < 0 ? 0 : (n > 396 ? 396 : n); }   // group start kept inside the frame
+constexpr TcFoldTable tc_make_fold_table() {
+    TcFoldTable t{};
+    for (int sweep = 0; sweep < 2; ++sweep)
+        for (int j = 0; j < kTcChunks; ++j) {
+            TcFoldChunk& c = t.c[sweep][j];
+            const int r0 = 8 * j;
             for (int i = 0; i < 8; ++i) {
-                const bool live = i < last;
-                a[i] = live ? fr[tc_off(live ? 100 - r0 - i : 0)] : 0.f;
-                b[i] = live ? fr[tc_off(live ? 300 + r0 + i : 0)] : 0.f;
-                c[i] = live ? fr[tc_off(live ? 100 + r0 + i : 0)] : 0.f;
-                d[i] = live ? fr[tc_off(live ? 300 - r0 - i : 0)] : 0.f;
+                const int n = sweep == 0 ? r0 + i : 100 - r0 - i;
+                const bool live = n >= 0 && n <= 200;
+                c.wa[i] = live ? kTcWindow.v[n] : 0.0f;
+                c.wb[i] = live ? (sweep == 0 ? kTcWindow.v[200 - n] : -kTcWindow.v[200 - n]) : 0.0f;
+            }
+            // ascending runs start at A0, A1; descending runs start (head) at D0, D1 and go down
+            const int A0 = sweep == 0 ? r0 : 300 + r0, A1 = sweep == 0 ? 200 + r0 : 100 + r0;
+            const int D0 = sweep == 0 ? 400 - r0 : 100 - r0, D1 = sweep == 0 ? 200 - r0 : 300 - r0;
+            const int A[2] = {A0, A1}, D[2] = {D0, D1};
+            for (int q = 0; q < 2; ++q) {
+                c.asc[q][0] = 4 * tc_off(tc_clamp_sample(A[q]));
+                c.asc[q][1] = 4 * tc_off(tc_clamp_sample(A[q] + 4));
+                c.head[q] = 4 * tc_off(D[q] > 399 ? 0 : (D[q] < 0 ? 0 : D[q]));   // x[400] (weight 0): any in-frame sample
+                c.desc[q][0] = 4 * tc_off(tc_clamp_sample(D[q] - 4));
+                c.desc[q][1] = 4 * tc_off(tc_clamp_sample(D[q] - 8));
             }
         }
-    }
+    return t;
 }
 
-// The chunk: packed hi/lo columns for the sweep's first unit (0 or 2) and second unit (1 or 3);
-// column c of the chunk holds slots 8 J + 2c, 8 J + 2c + 1.
-template <int SWEEP, int J>
-B200_HD void tc_sweep_chunk(const float* fr, uint32_t (&hi_first)[4], uint32_t (&lo_first)[4],
+B200_HD TcF4 tc_ld4_bytes(const float* fr, int byte_off) {
+    TcF4 r;
+#if defined(__CUDA_ARCH__)
+    const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(fr) + byte_off);
+    r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+#else
+    for (int i = 0; i < 4; ++i) r.v[i] = fr[byte_off / 4 + i];
+#endif
+    return r;
+}
+
+// The chunk: packed hi/lo columns for the sweep's first unit (0 or 2) and second unit (1 or 3); column q of the
+// chunk holds slots 8 J + 2q, 8 J + 2q + 1.  sign = +1 (E sweep) or -1 (O sweep).
+B200_HD void tc_sweep_chunk(const float* fr, const TcFoldChunk& fc, float sign, uint32_t (&hi_first)[4], uint32_t (&lo_first)[4],
                             uint32_t (&hi_second)[4], uint32_t (&lo_second)[4]) {
-    float a[8], b[8], c[8], d[8], first[8], second[8];
-    tc_gather<SWEEP, J>(fr, a, b, c, d);
-#define B200_TC_POINT(I)                                                              \
-    {                                                                                 \
-        float plus, minus;                                                            \
-        tc_point<SWEEP, 8 * J + I>(a[I], b[I], c[I], d[I], plus, minus);              \
-        first[I] = SWEEP == 0 ? plus : minus;                                         \
-        second[I] = SWEEP == 0 ? minus : plus;                                        \
+    float up[2][8], down[2][8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const TcF4 u0 = tc_ld4_bytes(fr, fc.asc[q][0]), u1 = tc_ld4_bytes(fr, fc.asc[q][1]);
+        const TcF4 d0 = tc_ld4_bytes(fr, fc.desc[q][0]), d1 = tc_ld4_bytes(fr, fc.desc[q][1]);
+        down[q][0] = fr[fc.head[q] / 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { up[q][i] = u0.v[i]; up[q][4 + i] = u1.v[i]; down[q][1 + i] = d0.v[3 - i]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) down[q][5 + i] = d1.v[3 - i];
     }
-    B200_TC_POINT(0) B200_TC_POINT(1) B200_TC_POINT(2) B200_TC_POINT(3)
-    B200_TC_POINT(4) B200_TC_POINT(5) B200_TC_POINT(6) B200_TC_POINT(7)
-#undef B200_TC_POINT
+    // E: sa = x[n] + x[400-n] = up0 + down0, sb = x[200-n] + x[200+n] = down1 + up1
+    // O: sa = x[n] - x[400-n] = down0 - up0, sb = x[200-n] - x[200+n] = up1 - down1
+    float first[8], second[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float sa = fmaf(sign, up[0][i], down[0][i]);
+        const float sb = fmaf(sign, down[1][i], up[1][i]);
+        const float t = fc.wa[i] * sa;
+        first[i] = fmaf(fc.wb[i], sb, t);
+        second[i] = fmaf(-fc.wb[i], sb, t);
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         tc_split_pack(first[2 * q], first[2 * q + 1], hi_first[q], lo_first[q]);

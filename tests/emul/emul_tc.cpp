@@ -48,27 +48,27 @@ float unit_column(const TcTables& tab, const std::vector<uint32_t>& tmem, int f,
     return static_cast<float>(acc);
 }
 
-template <int SWEEP, int J>
-void sweep_chunk_to_tmem(const float* fr, uint32_t* lane) {
-    uint32_t hf[4], lf[4], hs[4], ls[4];
-    tc_sweep_chunk<SWEEP, J>(fr, hf, lf, hs, ls);
-    constexpr int u1 = SWEEP == 0 ? 0 : 2, u2 = u1 + 1;
-    if (J < 12) {
-        for (int q = 0; q < 4; ++q) {
-            lane[tc_hi_col(u1) + 4 * J + q] = hf[q]; lane[tc_lo_col(u1) + 4 * J + q] = lf[q];
-            lane[tc_hi_col(u2) + 4 * J + q] = hs[q]; lane[tc_lo_col(u2) + 4 * J + q] = ls[q];
-        }
-    } else {
-        for (int q = 0; q < 3; ++q) {
-            lane[tc_left_col(u1) + q] = hf[q]; lane[tc_left_col(u1) + 3 + q] = lf[q];
-            lane[tc_left_col(u2) + q] = hs[q]; lane[tc_left_col(u2) + 3 + q] = ls[q];
+constexpr TcFoldTable kFold = tc_make_fold_table();
+
+// one sweep of one frame, stored to the emulated tensor-memory lane exactly like the kernel's fold warps do
+void sweep_to_tmem(int sweep, const float* fr, uint32_t* lane) {
+    const int u1 = 2 * sweep, u2 = u1 + 1;
+    const float sign = sweep == 0 ? 1.0f : -1.0f;
+    for (int j = 0; j < kTcChunks; ++j) {
+        uint32_t hf[4], lf[4], hs[4], ls[4];
+        tc_sweep_chunk(fr, kFold.c[sweep][j], sign, hf, lf, hs, ls);
+        if (j < 2 * kTcMainSteps) {
+            for (int q = 0; q < 4; ++q) {
+                lane[tc_hi_col(u1) + 4 * j + q] = hf[q]; lane[tc_lo_col(u1) + 4 * j + q] = lf[q];
+                lane[tc_hi_col(u2) + 4 * j + q] = hs[q]; lane[tc_lo_col(u2) + 4 * j + q] = ls[q];
+            }
+        } else {
+            for (int q = 0; q < 3; ++q) {
+                lane[tc_left_col(u1) + q] = hf[q]; lane[tc_left_col(u1) + 3 + q] = lf[q];
+                lane[tc_left_col(u2) + q] = hs[q]; lane[tc_left_col(u2) + 3 + q] = ls[q];
+            }
         }
     }
-}
-
-template <int SWEEP, int... J>
-void sweep_to_tmem(const float* fr, uint32_t* lane, std::integer_sequence<int, J...>) {
-    (sweep_chunk_to_tmem<SWEEP, J>(fr, lane), ...);
 }
 
 template <int NM, int U>
@@ -114,8 +114,8 @@ int run(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
         for (int f = 0; f < kTcTileFrames; ++f) {
             const float* fr = s_audio.data() + f * kTcRowPitch;
             uint32_t* lane = tmem.data() + f * 512;
-            sweep_to_tmem<0>(fr, lane, std::make_integer_sequence<int, kTcChunks>{});
-            sweep_to_tmem<1>(fr, lane, std::make_integer_sequence<int, kTcChunks>{});
+            sweep_to_tmem(0, fr, lane);
+            sweep_to_tmem(1, fr, lane);
         }
         for (int f = 0; f < kTcTileFrames && t0 + f < n_frames; ++f) {
             float acc0[L::acc_size(0)] = {0.f}, acc1[L::acc_size(1)] = {0.f};
@@ -168,8 +168,8 @@ extern "C" int emul_tc_frame_spectrum(const float* frame400, double* re, double*
     std::vector<float> s_audio(3 * kTcRowPitch, 0.f);
     for (int n = 0; n < kNFFT; ++n) s_audio[tc_off(n)] = frame400[n];
     std::vector<uint32_t> tmem(512, 0u);
-    sweep_to_tmem<0>(s_audio.data(), tmem.data(), std::make_integer_sequence<int, kTcChunks>{});
-    sweep_to_tmem<1>(s_audio.data(), tmem.data(), std::make_integer_sequence<int, kTcChunks>{});
+    sweep_to_tmem(0, s_audio.data(), tmem.data());
+    sweep_to_tmem(1, s_audio.data(), tmem.data());
     for (int u = 0; u < kTcUnits; ++u) {
         for (int kp = 0; kp < kTcBinsPerUnit; ++kp) {
             const int bin = tc_unit_bin(u, kp);
