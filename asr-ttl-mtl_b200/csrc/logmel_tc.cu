@@ -36,7 +36,8 @@ namespace {
 constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpProducer = 17;   // producers: warps 17..19
 constexpr int kTcWarps = 20;
 constexpr int kTcThreads = kTcWarps * 32;   // 640
-constexpr uint32_t kSpinLimit = 1u << 24;    // a protocol bug traps instead of hanging the device
+constexpr uint32_t kSpinLimit = 1u << 22;    // a protocol bug traps instead of hanging the device
+constexpr uint32_t kWaitHintNs = 20000;      // suspend-time hint of one try_wait
 
 // Bring-up timeline (B200MEL_TC_TRACE=1): CTA 0 stamps clock64() at the hand-over points of its first tiles.
 constexpr int kTraceTiles = 8, kTraceEvents = 16, kTraceRoles = 6;
@@ -54,6 +55,8 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Waits are potentially-blocking try_waits with a suspend-time hint: the hardware parks the warp until the phase
+// completes (or the hint expires), so a waiting role does not burn issue slots of the roles that are working.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0, spins = 0;
@@ -61,9 +64,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity), "r"(kWaitHintNs) : "memory");
         if (done) break;
         if (++spins > kSpinLimit) __trap();
     }
@@ -203,13 +206,15 @@ __device__ __forceinline__ TileCoord tile_coord(int64_t tile, int tiles_per_clip
     return c;
 }
 
-// ---- producers: one tile of audio into shared memory ---------------------------------------------
-// 96 threads (3 warps) move the tile as 5200 16-byte chunks (130 rows x 40) with cp.async (LDGSTS, L1
-// bypass): the source is one contiguous span, the destination rows sit at pitch 164 words.  A chunk that
-// touches a clip edge (reflect padding, zero tail, `lengths`), an unaligned row or int16 PCM is written by
-// hand.  Completion: every thread's copies arrive on `full` through cp.async.mbarrier.arrive.noinc, its
-// plain stores through a normal (release) arrive - the barrier expects 2 x 96 arrivals per tile.
-constexpr int kProducerThreads = 96;
+// ---- loaders: one tile of audio into shared memory -----------------------------------------------
+// 352 threads (the 8 fold warps, which would otherwise idle until the tile is there, plus 3 helper warps) move
+// the tile as 5200 16-byte chunks (130 rows x 40) with cp.async (LDGSTS, L1 bypass) - many threads because the
+// copy rate is set by how many requests are in flight.  The source is one contiguous span, the destination rows
+// sit at pitch 164 words.  A chunk that touches a clip edge (reflect padding, zero tail, `lengths`), an unaligned
+// row or int16 PCM is written by hand.  Completion: every thread's copies arrive on `full` through
+// cp.async.mbarrier.arrive.noinc, its plain stores through a normal (release) arrive - the barrier expects
+// 2 x 352 arrivals per tile.
+constexpr int kProducerThreads = 352;
 constexpr int kChunksPerRow = kHop / 4;                       // 40
 constexpr int kTileChunks = kTcAudioRows * kChunksPerRow;     // 5200
 
@@ -243,14 +248,14 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
     const bool aligned = sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
     const uint32_t dst0 = smem_u32(s_audio);
     // chunk c = 40 r + k covers samples s0 + 4c .. + 3 and lands at word 164 r + 4 k
-    int r = pt / kChunksPerRow, k = pt - r * kChunksPerRow;   // pt < 96: r in {0, 1, 2}
+    int r = pt / kChunksPerRow, k = pt - r * kChunksPerRow;
     if (aligned && s0 >= 0 && s0 + kTcAudioRows * kHop <= valid) {
         const float* src = reinterpret_cast<const float*>(row) + s0 + 4 * pt;
 #pragma unroll 4
         for (int c = pt; c < kTileChunks; c += kProducerThreads) {
             cp_async16(dst0 + 4u * static_cast<uint32_t>(r * kTcRowPitch + 4 * k), src);
             src += 4 * kProducerThreads;
-            r += 2; k += 16;                                   // 96 = 2 x 40 + 16
+            r += 8; k += 32;                                   // 352 = 8 x 40 + 32
             if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
         }
     } else {
@@ -272,7 +277,7 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
                     }
                 }
             }
-            r += 2; k += 16;
+            r += 8; k += 32;
             if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
         }
     }
@@ -283,23 +288,23 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
 // ---- fold warps: one sweep of one tile, A operand -> tensor memory -----------------------------------
 __constant__ TcFoldTable c_fold = tc_make_fold_table();
 
-// One compact loop serves both sweeps (the E and the O warps run the same instructions on different table rows
-// and tensor-memory columns), so the fold code stays resident in the instruction caches.
-__device__ __forceinline__ void sweep_store(int sweep, const float* fr, uint32_t lane_addr) {
-    const TcFoldChunk* __restrict__ table = c_fold.c[sweep];
-    const float sign = sweep == 0 ? 1.0f : -1.0f;
-    const uint32_t u1 = lane_addr + tc_hi_col(2) * sweep;          // hi block of the sweep's first unit (0 or 2)
+// A compact 12-iteration loop per sweep (not 13 unrolled chunks): the fold code stays resident in the instruction
+// caches, and the table rows are read with warp-uniform constant loads.
+template <int SWEEP>
+__device__ __forceinline__ void sweep_store(const float* fr, uint32_t lane_addr) {
+    const TcFoldChunk* __restrict__ table = c_fold.c[SWEEP];
+    const uint32_t u1 = lane_addr + tc_hi_col(2 * SWEEP);          // hi block of the sweep's first unit (0 or 2)
     uint32_t hf[4], lf[4], hs[4], ls[4];
 #pragma unroll 1
     for (int j = 0; j < 2 * kTcMainSteps; ++j) {                   // slots 8j..8j+7 of the main blocks
-        tc_sweep_chunk(fr, table[j], sign, hf, lf, hs, ls);
+        tc_sweep_chunk<SWEEP>(fr, table[j], hf, lf, hs, ls);
         const uint32_t c = u1 + 4 * j;
         tmem_st4(c, hf); tmem_st4(c + 48, lf);                     // unit: [hi 48 | lo 48], next unit 96 columns on
         tmem_st4(c + 96, hs); tmem_st4(c + 144, ls);
     }
-    tc_sweep_chunk(fr, table[2 * kTcMainSteps], sign, hf, lf, hs, ls);
+    tc_sweep_chunk<SWEEP>(fr, table[2 * kTcMainSteps], hf, lf, hs, ls);
     // slots 96..101: [hi x 3 | lo x 3] columns of the leftover area, second unit 6 columns on
-    const uint32_t b1 = lane_addr + tc_left_col(0) + (tc_left_col(2) - tc_left_col(0)) * sweep, b2 = b1 + 6;
+    const uint32_t b1 = lane_addr + tc_left_col(2 * SWEEP), b2 = b1 + 6;
     tmem_st2(b1, hf[0], hf[1]); tmem_st2(b1 + 2, hf[2], lf[0]); tmem_st2(b1 + 4, lf[1], lf[2]);
     tmem_st2(b2, hs[0], hs[1]); tmem_st2(b2 + 2, hs[2], ls[0]); tmem_st2(b2 + 4, ls[1], ls[2]);
 }
@@ -365,19 +370,23 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
         const int f = quad * 32 + lane, t = tc.t0 + f;
         const bool live = t < a.n_frames;
         constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
-        float* out = a.out + (tc.clip * NM + m_begin) * static_cast<int64_t>(a.n_frames) + t;
+        const int64_t pitch = a.n_frames;
+        float* out = a.out + (tc.clip * NM + m_begin) * pitch + t;
         float mx = __uint_as_float(0xff800000u);
+        if (live) {
 #pragma unroll
-        for (int m = m_begin; m < m_end; ++m) {
-            const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
-            if (live) { if (debug_stage != 5) *out = lg; mx = max_nan(mx, lg); }
-            out += a.n_frames;
+            for (int m = m_begin; m < m_end; ++m) {
+                const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
+                *out = lg;
+                out += pitch;
+                mx = max_nan(mx, lg);
+            }
         }
 #pragma unroll
         for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
         uint32_t key = live ? max_key_encode(mx) : 0u;
         key = __reduce_max_sync(0xffffffffu, key);
-        if (lane == 0 && debug_stage != 5) atomicMax(a.max_keys + (a.global_max ? 0 : tc.clip), key);
+        if (lane == 0) atomicMax(a.max_keys + (a.global_max ? 0 : tc.clip), key);
         if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
     }
 }
@@ -396,7 +405,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
     const int tiles_per_clip = (a.n_frames + kTcTileFrames - 1) / kTcTileFrames;
     int64_t total_tiles = a.batch * tiles_per_clip;
     // bring-up aid (B200MEL_TC_DEBUG): 1 = setup only, 2 = + producer and folds of ONE tile,
-    // 3 = + the tensor cores, 4 = + accumulator loads, 5 = + epilogue math, 6 = everything for one tile
+    // 3 = + the tensor cores, 4 = + accumulator loads, 6 = everything for one tile
     if (debug_stage > 0 && debug_stage != 7 && total_tiles > gridDim.x) total_tiles = gridDim.x;
     if (debug_stage == 1) total_tiles = 0;
 
@@ -446,12 +455,14 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
         int ti = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
             if (quad == 0) TC_TRACE(1 + sweep, ti, 0);
+            mbar_wait(&bars.audio_empty, parity ^ 1u);      // every fold warp has finished reading the previous tile
+            produce_tile<InT>(a, tile_coord(tile, tiles_per_clip), s_audio, &bars.audio_full, tid);
             mbar_wait(&bars.audio_full, parity);
             if (quad == 0) TC_TRACE(1 + sweep, ti, 1);
             mbar_wait(&bars.a_empty[sweep], parity ^ 1u);   // the tensor cores are done with the previous tile's operand
             if (quad == 0) TC_TRACE(1 + sweep, ti, 2);
             tc_fence_after();
-            sweep_store(sweep, fr, lane_addr);
+            if (sweep == 0) sweep_store<0>(fr, lane_addr); else sweep_store<1>(fr, lane_addr);
             if (quad == 0) TC_TRACE(1 + sweep, ti, 3);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
@@ -501,18 +512,18 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
             if (debug_stage == 3 && total_tiles > 0) mbar_wait(&bars.d_full, 1);   // nobody drains the accumulator in this stage
         } else if (warp >= kWarpProducer) {
             // ===== audio producers =====
-            const int pt = tid - kWarpProducer * 32;
+            const int pt = tid - kWarpProducer * 32 + kWarpEpi0 * 32;   // loader index after the 256 fold threads
             uint32_t parity = 1;   // audio_empty: the first wait passes
             int ti = 0;
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-                if (pt == 0) TC_TRACE(0, ti, 0);
+                if (lane == 0 && warp == kWarpProducer) TC_TRACE(0, ti, 0);
                 // while waiting for the buffer, pull the NEXT tile towards L2 (the current one was prefetched a tile ago)
-                if (pt == 0 && tile + gridDim.x < total_tiles) prefetch_tile_l2<InT>(a, tile_coord(tile + gridDim.x, tiles_per_clip));
+                if (lane == 0 && warp == kWarpProducer && tile + gridDim.x < total_tiles) prefetch_tile_l2<InT>(a, tile_coord(tile + gridDim.x, tiles_per_clip));
                 mbar_wait(&bars.audio_empty, parity);
-                if (pt == 0) TC_TRACE(0, ti, 1);
+                if (lane == 0 && warp == kWarpProducer) TC_TRACE(0, ti, 1);
                 parity ^= 1u;
                 produce_tile<InT>(a, tile_coord(tile, tiles_per_clip), s_audio, &bars.audio_full, pt);
-                if (pt == 0) TC_TRACE(0, ti, 2);
+                if (lane == 0 && warp == kWarpProducer) TC_TRACE(0, ti, 2);
             }
         }
         __syncwarp();

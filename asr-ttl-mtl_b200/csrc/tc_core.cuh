@@ -127,9 +127,18 @@ B200_HD uint32_t tc_half2_bits(__half2 h) {
 // (v0, v1) -> packed hi pair and packed lo pair, v = hi + lo up to 2^-22 relative
 B200_HD void tc_split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(v0, v1);
-    const float2 hf = __half22float2(h);
     hi = tc_half2_bits(h);
+#if defined(__CUDA_ARCH__)
+    // v - hi in one mixed-precision add each (SASS FHADD, sm_100+): 2 instructions per value for the whole split
+    float r0, r1;
+    asm("{\n.reg .b16 l, u, nl, nu;\nmov.b32 {l, u}, %2;\nneg.f16 nl, l;\nneg.f16 nu, u;\n"
+        "add.rn.f32.f16 %0, nl, %3;\nadd.rn.f32.f16 %1, nu, %4;\n}\n"
+        : "=f"(r0), "=f"(r1) : "r"(hi), "f"(v0), "f"(v1));
+    lo = tc_half2_bits(__floats2half2_rn(r0, r1));
+#else
+    const float2 hf = __half22float2(h);
     lo = tc_half2_bits(__floats2half2_rn(v0 - hf.x, v1 - hf.y));
+#endif
 }
 
 // ---- one sweep chunk: 8 slots of both units of a sweep, table driven -----------------------------------
@@ -192,8 +201,9 @@ B200_HD TcF4 tc_ld4_bytes(const float* fr, int byte_off) {
 }
 
 // The chunk: packed hi/lo columns for the sweep's first unit (0 or 2) and second unit (1 or 3); column q of the
-// chunk holds slots 8 J + 2q, 8 J + 2q + 1.  sign = +1 (E sweep) or -1 (O sweep).
-B200_HD void tc_sweep_chunk(const float* fr, const TcFoldChunk& fc, float sign, uint32_t (&hi_first)[4], uint32_t (&lo_first)[4],
+// chunk holds slots 8 J + 2q, 8 J + 2q + 1.
+template <int SWEEP>
+B200_HD void tc_sweep_chunk(const float* fr, const TcFoldChunk& fc, uint32_t (&hi_first)[4], uint32_t (&lo_first)[4],
                             uint32_t (&hi_second)[4], uint32_t (&lo_second)[4]) {
     float up[2][8], down[2][8];
 #pragma unroll
@@ -211,8 +221,8 @@ B200_HD void tc_sweep_chunk(const float* fr, const TcFoldChunk& fc, float sign, 
     float first[8], second[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float sa = fmaf(sign, up[0][i], down[0][i]);
-        const float sb = fmaf(sign, down[1][i], up[1][i]);
+        const float sa = SWEEP == 0 ? down[0][i] + up[0][i] : down[0][i] - up[0][i];
+        const float sb = SWEEP == 0 ? up[1][i] + down[1][i] : up[1][i] - down[1][i];
         const float t = fc.wa[i] * sa;
         first[i] = fmaf(fc.wb[i], sb, t);
         second[i] = fmaf(-fc.wb[i], sb, t);

@@ -53,10 +53,10 @@ constexpr TcFoldTable kFold = tc_make_fold_table();
 // one sweep of one frame, stored to the emulated tensor-memory lane exactly like the kernel's fold warps do
 void sweep_to_tmem(int sweep, const float* fr, uint32_t* lane) {
     const int u1 = 2 * sweep, u2 = u1 + 1;
-    const float sign = sweep == 0 ? 1.0f : -1.0f;
     for (int j = 0; j < kTcChunks; ++j) {
         uint32_t hf[4], lf[4], hs[4], ls[4];
-        tc_sweep_chunk(fr, kFold.c[sweep][j], sign, hf, lf, hs, ls);
+        if (sweep == 0) tc_sweep_chunk<0>(fr, kFold.c[0][j], hf, lf, hs, ls);
+        else tc_sweep_chunk<1>(fr, kFold.c[1][j], hf, lf, hs, ls);
         if (j < 2 * kTcMainSteps) {
             for (int q = 0; q < 4; ++q) {
                 lane[tc_hi_col(u1) + 4 * j + q] = hf[q]; lane[tc_lo_col(u1) + 4 * j + q] = lf[q];
