@@ -267,7 +267,10 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     a.done_counters = keys + batch;
     a.tile_counter = keys + 2 * batch;
     a.global_max = global_max;
-    a.fused_norm = (variant == B200MEL_VARIANT_FFT && !global_max && tiles_per_clip <= kMaxFusedNormTiles) ? 1 : 0;
+    // one max per utterance (or a single utterance, where the call's max is the utterance's): normalised inside the
+    // front-end kernel.  The FFT variant's last CTA normalises the whole utterance, so very long ones go to pass 2;
+    // the tcgen05 variant normalises tile by tile and has no such limit.
+    a.fused_norm = ((!global_max || batch == 1) && (variant == B200MEL_VARIANT_TCGEN05 || tiles_per_clip <= kMaxFusedNormTiles)) ? 1 : 0;
     a.n_rows = plan->n_rows;
     a.tables = plan->d_tables;
     if (variant == B200MEL_VARIANT_TCGEN05)

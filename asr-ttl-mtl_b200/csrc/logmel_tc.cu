@@ -3,10 +3,10 @@
 // reference: whisper/audio.py:145-155).
 //
 // One persistent CTA per SM, warp-specialised, no __syncthreads in the steady state (mbarriers only):
-//   3 producer warps: stage the tile's 130 rows of 160 samples in shared memory at pitch 164 words with 16-byte
-//                     cp.async copies that complete on an mbarrier; chunks that touch a clip edge (reflect
-//                     padding, zero tail, `lengths`) or are not 16-byte aligned are written by hand;
-//   4 + 4 fold warps: one thread per frame (= TMEM lane).  The E warps compute ee / eo, the O warps oe / oo
+//   4 + 4 fold warps: first stage the tile's 130 rows of 160 samples in shared memory at pitch 164 words with 16-byte
+//                     cp.async copies that complete on an mbarrier (next tile prefetched into L2; chunks that touch
+//                     a clip edge - reflect padding, zero tail, `lengths` - or are unaligned are written by hand);
+//                     then one thread per frame (= TMEM lane).  The E warps compute ee / eo, the O warps oe / oo
 //                     (window multiply and both folds fused: 5 flops per two values), split every value
 //                     into fp16 hi + lo and write the packed pairs straight into TENSOR MEMORY as the
 //                     A operand (tcgen05.st) - the data never touch shared memory again;
@@ -20,7 +20,10 @@
 //                     partial sums in registers; after the 4th unit: log10(max(., 1e-10)), 128-byte
 //                     coalesced row stores and the utterance's max key (warp REDUX + one atomicMax).
 // Tensor memory is exactly full: 408 operand columns (4 units x [hi | lo], tc_core.cuh) + 104 accumulator.
-// The (max - 8, (x + 4) / 4) step runs as the shared pass-2 kernel.
+//   3 normaliser    : the epilogue warp that completes an utterance (per-clip counter) queues it; these warps apply
+//     warps           max(x, g - 8), (x + 4) / 4 in place while the utterance's 0.96 MB is still L2-resident, so the
+//                     front-end is one launch whose DRAM traffic is the algorithmic read + write.
+// (One max over the whole call, or very long utterances: the shared pass-2 kernel normalises instead.)
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -33,10 +36,10 @@ namespace b200mel {
 
 namespace {
 
-constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpProducer = 17;   // producers: warps 17..19
+constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpNorm = 17;   // normalisers: warps 17..19
 constexpr int kTcWarps = 20;
 constexpr int kTcThreads = kTcWarps * 32;   // 640
-constexpr uint32_t kSpinLimit = 1u << 22;    // a protocol bug traps instead of hanging the device
+constexpr uint32_t kSpinLimit = 1u << 17;    // x 20 us hint = 2.6 s: a protocol bug traps instead of hanging the device
 constexpr uint32_t kWaitHintNs = 20000;      // suspend-time hint of one try_wait
 
 // Bring-up timeline (B200MEL_TC_TRACE=1): CTA 0 stamps clock64() at the hand-over points of its first tiles.
@@ -57,6 +60,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Waits are potentially-blocking try_waits with a suspend-time hint: the hardware parks the warp until the phase
 // completes (or the hint expires), so a waiting role does not burn issue slots of the roles that are working.
+// Bring-up aid: a wait that exceeds the spin limit records (CTA, barrier offset, parity, warp) in a host-mapped word
+// before it traps, so the host can name the hand-over that hung (b200mel_last_cuda_error).
+__device__ unsigned* g_tc_fault = nullptr;
+__device__ __noinline__ void tc_fault(uint32_t code) {
+    if (g_tc_fault != nullptr) {
+        g_tc_fault[0] = code;
+        g_tc_fault[1] = blockIdx.x;
+        __threadfence_system();
+    }
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0, spins = 0;
@@ -68,21 +82,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n"
             "}\n" : "=r"(done) : "r"(addr), "r"(parity), "r"(kWaitHintNs) : "memory");
         if (done) break;
-        if (++spins > kSpinLimit) __trap();
+        if (++spins > kSpinLimit) tc_fault(0x1000000u | ((addr & 0xfffu) << 12) | (parity << 8) | (threadIdx.x >> 5));
     }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // ---- tensor memory stores / loads (32 lanes x 32 bit per column, this warp's lane quadrant) ----
+// The stores carry no "memory" clobber: they alias nothing the compiler can see, and their ordering against the
+// tensor cores comes from tcgen05.wait::st + the fences, so shared-memory loads may be scheduled across them.
 __device__ __forceinline__ void tmem_st1(uint32_t t, uint32_t a) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(t), "r"(a) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(t), "r"(a));
 }
 __device__ __forceinline__ void tmem_st2(uint32_t t, uint32_t a, uint32_t b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t), "r"(a), "r"(b) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t), "r"(a), "r"(b));
 }
 __device__ __forceinline__ void tmem_st4(uint32_t t, const uint32_t (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]));
 }
 __device__ __forceinline__ void tmem_ld4(uint32_t t, float* d) {
     uint32_t r[4];
@@ -194,6 +210,52 @@ struct TcBarriers {
     uint64_t d_full, d_empty;
 };
 
+// ---- normaliser warps ------------------------------------------------------------------------------
+// In-place dynamic-range clamp + affine map (audio.py:155-156) of ONE TILE of a finished utterance: the rows this
+// CTA's epilogue wrote a few tile periods ago, read back through L2.  Every CTA normalises its own tiles, so the work
+// is spread exactly like the tiles are; nothing is queued.
+constexpr int kNormThreadsTc = 96;
+
+__device__ __forceinline__ float4 normalise4(float4 x, float g) {
+    x.x = normalise(x.x, g); x.y = normalise(x.y, g); x.z = normalise(x.z, g); x.w = normalise(x.w, g);
+    return x;
+}
+
+template <int NM>
+__device__ __forceinline__ void normalise_tile_tc(float* __restrict__ tile_out, int64_t pitch, int frames, float g, int nt) {
+    const int w = nt >> 5, lane = nt & 31;
+    if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & 15u) == 0) {
+        // a warp takes whole mel rows (lane = float4 column, 512 contiguous bytes), four rows in flight
+        if (lane < (frames >> 2)) {
+            float* p = tile_out + w * pitch + 4 * lane;
+            const int64_t step = 3 * pitch;
+            int row = w;
+#pragma unroll 1
+            for (; row + 9 < NM; row += 12, p += 4 * step) {
+                float4 x0 = __ldcg(reinterpret_cast<float4*>(p)), x1 = __ldcg(reinterpret_cast<float4*>(p + step));
+                float4 x2 = __ldcg(reinterpret_cast<float4*>(p + 2 * step)), x3 = __ldcg(reinterpret_cast<float4*>(p + 3 * step));
+                *reinterpret_cast<float4*>(p) = normalise4(x0, g);
+                *reinterpret_cast<float4*>(p + step) = normalise4(x1, g);
+                *reinterpret_cast<float4*>(p + 2 * step) = normalise4(x2, g);
+                *reinterpret_cast<float4*>(p + 3 * step) = normalise4(x3, g);
+            }
+#pragma unroll 1
+            for (; row < NM; row += 3, p += step) *reinterpret_cast<float4*>(p) = normalise4(__ldcg(reinterpret_cast<float4*>(p)), g);
+        }
+        const int rest = frames & 3;                                           // 0 for whole clips (pitch % 4 == 0)
+        if (rest != 0)
+            for (int i = nt; i < NM * rest; i += kNormThreadsTc) {
+                float* q = tile_out + (i / rest) * pitch + (frames & ~3) + i % rest;
+                *q = normalise(__ldcg(q), g);
+            }
+    } else {
+        for (int i = nt; i < NM * frames; i += kNormThreadsTc) {
+            float* q = tile_out + (i / frames) * pitch + i % frames;
+            *q = normalise(__ldcg(q), g);
+        }
+    }
+}
+
 template <typename InT> __device__ __forceinline__ float sample_to_float(InT v);
 template <> __device__ __forceinline__ float sample_to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float sample_to_float<int16_t>(int16_t v) { return static_cast<float>(v) * (1.0f / 32768.0f); }
@@ -207,14 +269,14 @@ __device__ __forceinline__ TileCoord tile_coord(int64_t tile, int tiles_per_clip
 }
 
 // ---- loaders: one tile of audio into shared memory -----------------------------------------------
-// 352 threads (the 8 fold warps, which would otherwise idle until the tile is there, plus 3 helper warps) move
+// The 256 fold threads (which would otherwise idle until the tile is there) move
 // the tile as 5200 16-byte chunks (130 rows x 40) with cp.async (LDGSTS, L1 bypass) - many threads because the
 // copy rate is set by how many requests are in flight.  The source is one contiguous span, the destination rows
 // sit at pitch 164 words.  A chunk that touches a clip edge (reflect padding, zero tail, `lengths`), an unaligned
 // row or int16 PCM is written by hand.  Completion: every thread's copies arrive on `full` through
 // cp.async.mbarrier.arrive.noinc, its plain stores through a normal (release) arrive - the barrier expects
-// 2 x 352 arrivals per tile.
-constexpr int kProducerThreads = 352;
+// 2 x 256 arrivals per tile.
+constexpr int kProducerThreads = 256;
 constexpr int kChunksPerRow = kHop / 4;                       // 40
 constexpr int kTileChunks = kTcAudioRows * kChunksPerRow;     // 5200
 
@@ -255,7 +317,7 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
         for (int c = pt; c < kTileChunks; c += kProducerThreads) {
             cp_async16(dst0 + 4u * static_cast<uint32_t>(r * kTcRowPitch + 4 * k), src);
             src += 4 * kProducerThreads;
-            r += 8; k += 32;                                   // 352 = 8 x 40 + 32
+            r += 6; k += 16;                                   // 256 = 6 x 40 + 16
             if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
         }
     } else {
@@ -277,7 +339,7 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
                     }
                 }
             }
-            r += 8; k += 32;
+            r += 6; k += 16;
             if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
         }
     }
@@ -295,7 +357,7 @@ __device__ __forceinline__ void sweep_store(const float* fr, uint32_t lane_addr)
     const TcFoldChunk* __restrict__ table = c_fold.c[SWEEP];
     const uint32_t u1 = lane_addr + tc_hi_col(2 * SWEEP);          // hi block of the sweep's first unit (0 or 2)
     uint32_t hf[4], lf[4], hs[4], ls[4];
-#pragma unroll 1
+#pragma unroll 2
     for (int j = 0; j < 2 * kTcMainSteps; ++j) {                   // slots 8j..8j+7 of the main blocks
         tc_sweep_chunk<SWEEP>(fr, table[j], hf, lf, hs, ls);
         const uint32_t c = u1 + 4 * j;
@@ -334,7 +396,8 @@ __device__ __forceinline__ void epilogue_unit(int unit, uint32_t d_addr, uint64_
 }
 
 template <int NM, int HALF>
-__device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, long long* trace, TcBarriers* bars, float* s_straddle,
+__device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, long long* trace, TcBarriers* bars,
+                                              float* s_straddle,
                                               uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
     using L = TcEpilogueLayout<NM>;
     constexpr int ACC = L::acc_size(HALF);
@@ -387,6 +450,13 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
         uint32_t key = live ? max_key_encode(mx) : 0u;
         key = __reduce_max_sync(0xffffffffu, key);
         if (lane == 0) atomicMax(a.max_keys + (a.global_max ? 0 : tc.clip), key);
+        if (a.fused_norm) {
+            // count this warp's share of the utterance: the normaliser warps of every CTA that holds one of its tiles
+            // wait for the count to be complete (8 epilogue warps per tile)
+            __threadfence();   // this tile's rows and max are visible before they are counted
+            __syncwarp();
+            if (lane == 0) atomicAdd(a.done_counters + tc.clip, 1u);
+        }
         if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
     }
 }
@@ -448,6 +518,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
     // (a setmaxnreg.inc can only take what another warpgroup released): folds 80 + 80, epilogue 144 + 144, rest 32
     if (warp < kWarpEpi0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        if (tid == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) prefetch_tile_l2<InT>(a, tile_coord(blockIdx.x, tiles_per_clip));
         // ===== fold warps: E sweep (warps 0-3) / O sweep (warps 4-7) =====
         const int sweep = warp < kWarpO ? 0 : 1;
         const float* fr = s_audio + (quad * 32 + lane) * kTcRowPitch;
@@ -455,6 +526,8 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
         int ti = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
             if (quad == 0) TC_TRACE(1 + sweep, ti, 0);
+            // while waiting for the buffer, pull the NEXT tile towards L2 (this one was asked for a tile ago)
+            if (tid == 0 && tile + gridDim.x < total_tiles) prefetch_tile_l2<InT>(a, tile_coord(tile + gridDim.x, tiles_per_clip));
             mbar_wait(&bars.audio_empty, parity ^ 1u);      // every fold warp has finished reading the previous tile
             produce_tile<InT>(a, tile_coord(tile, tiles_per_clip), s_audio, &bars.audio_full, tid);
             mbar_wait(&bars.audio_full, parity);
@@ -510,20 +583,28 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
                 a_parity ^= 1u;
             }
             if (debug_stage == 3 && total_tiles > 0) mbar_wait(&bars.d_full, 1);   // nobody drains the accumulator in this stage
-        } else if (warp >= kWarpProducer) {
-            // ===== audio producers =====
-            const int pt = tid - kWarpProducer * 32 + kWarpEpi0 * 32;   // loader index after the 256 fold threads
-            uint32_t parity = 1;   // audio_empty: the first wait passes
-            int ti = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-                if (lane == 0 && warp == kWarpProducer) TC_TRACE(0, ti, 0);
-                // while waiting for the buffer, pull the NEXT tile towards L2 (the current one was prefetched a tile ago)
-                if (lane == 0 && warp == kWarpProducer && tile + gridDim.x < total_tiles) prefetch_tile_l2<InT>(a, tile_coord(tile + gridDim.x, tiles_per_clip));
-                mbar_wait(&bars.audio_empty, parity);
-                if (lane == 0 && warp == kWarpProducer) TC_TRACE(0, ti, 1);
-                parity ^= 1u;
-                produce_tile<InT>(a, tile_coord(tile, tiles_per_clip), s_audio, &bars.audio_full, pt);
-                if (lane == 0 && warp == kWarpProducer) TC_TRACE(0, ti, 2);
+        } else if (warp >= kWarpNorm && a.fused_norm && debug_stage == 0) {
+            // ===== normaliser warps =====
+            // Walk this CTA's tiles a little behind the epilogue: once every tile of the utterance has been counted its
+            // max is final, and this CTA's own tile (still in L2) is clamped and rescaled in place.
+            const int nt = tid - kWarpNorm * 32;
+            const unsigned need = 8u * static_cast<unsigned>(tiles_per_clip);
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(tile, tiles_per_clip);
+                if (lane == 0) {
+                    uint32_t polls = 0;
+                    while (true) {
+                        unsigned seen;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.done_counters + tc.clip) : "memory");
+                        if (seen >= need) break;
+                        if (++polls > (1u << 22)) tc_fault(0x2000000u | (static_cast<uint32_t>(tile) << 8 & 0xffff00u) | (threadIdx.x >> 5));
+                        __nanosleep(500);
+                    }
+                }
+                __syncwarp();
+                const float g = max_key_decode(__ldcg(a.max_keys + tc.clip));
+                const int frames = a.n_frames - tc.t0 < kTcTileFrames ? a.n_frames - tc.t0 : kTcTileFrames;
+                normalise_tile_tc<NM>(a.out + tc.clip * NM * static_cast<int64_t>(a.n_frames) + tc.t0, a.n_frames, frames, g, nt);
             }
         }
         __syncwarp();
@@ -552,6 +633,19 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     const int tiles_per_clip = (a.n_frames + kTcTileFrames - 1) / kTcTileFrames;
     const int64_t tiles = a.batch * tiles_per_clip;
     const unsigned grid = static_cast<unsigned>(tiles < sms_by_device[device] ? tiles : sms_by_device[device]);
+    // bring-up aid: host-mapped fault words a timed-out wait fills in before trapping; reported at exit
+    static unsigned* fault_host = nullptr;
+    if (fault_host == nullptr && cudaHostAlloc(&fault_host, 64, cudaHostAllocMapped) == cudaSuccess) {
+        fault_host[0] = fault_host[1] = 0;
+        unsigned* fault_dev = nullptr;
+        if (cudaHostGetDevicePointer(&fault_dev, fault_host, 0) == cudaSuccess)
+            cudaMemcpyToSymbolAsync(g_tc_fault, &fault_dev, sizeof(fault_dev), 0, cudaMemcpyHostToDevice, stream);
+        static unsigned* fault_report = fault_host;
+        std::atexit([] {
+            if (fault_report[0] != 0)
+                std::fprintf(stderr, "b200mel tcgen05 kernel: wait timed out, code 0x%08x in CTA %u\n", fault_report[0], fault_report[1]);
+        });
+    }
     ProfileScope profile(2, stream);
     static const int debug_stage = std::getenv("B200MEL_TC_DEBUG") ? std::atoi(std::getenv("B200MEL_TC_DEBUG")) : 0;
     static long long* trace = nullptr;
