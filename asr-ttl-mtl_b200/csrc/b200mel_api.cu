@@ -211,10 +211,11 @@ int b200mel_plan_destroy(b200mel_plan* plan) {
 
 int b200mel_plan_n_mels(const b200mel_plan* plan) { return plan ? plan->n_mels : 0; }
 
-// workspace = [max keys: batch u32][completion counters: batch u32][tile queue head: 1 u32]
+// workspace = [max keys: batch u32][completion counters: batch u32][tile queue head: 1 u32][min keys: batch u32]
+static size_t workspace_words(int64_t batch) { return 3 * static_cast<size_t>(batch) + 1; }
 size_t b200mel_workspace_bytes(int64_t batch) {
     if (batch < 1) batch = 1;
-    return round_up((2 * static_cast<size_t>(batch) + 1) * sizeof(uint32_t), 256);
+    return round_up(workspace_words(batch) * sizeof(uint32_t), 256);
 }
 
 int b200mel_normalise_device(float* out, const void* workspace, int64_t batch, int64_t elems_per_clip,
@@ -247,7 +248,7 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int global_max = (flags & B200MEL_FLAG_GLOBAL_MAX) ? 1 : 0;
     uint32_t* keys = static_cast<uint32_t*>(workspace);
-    B200_CUDA(cudaMemsetAsync(keys, 0, (2 * static_cast<size_t>(batch) + 1) * sizeof(uint32_t), stream));
+    B200_CUDA(cudaMemsetAsync(keys, 0, workspace_words(batch) * sizeof(uint32_t), stream));
 
     const int64_t elems_per_clip = static_cast<int64_t>(plan->n_mels) * n_frames;
     const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
@@ -266,6 +267,7 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     a.max_keys = keys;
     a.done_counters = keys + batch;
     a.tile_counter = keys + 2 * batch;
+    a.min_keys = keys + 2 * batch + 1;
     a.global_max = global_max;
     // one max per utterance (or a single utterance, where the call's max is the utterance's): normalised inside the
     // front-end kernel.  The FFT variant's last CTA normalises the whole utterance, so very long ones go to pass 2;

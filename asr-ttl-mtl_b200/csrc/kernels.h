@@ -23,6 +23,8 @@ struct LogmelArgs {
     uint32_t* max_keys;      // device, [batch] (or [1] with global_max), order-preserving keys
     uint32_t* done_counters; // device, [batch]: warps that finished a tile of the utterance (fused normalise)
     uint32_t* tile_counter;  // device, [1]: the persistent kernel's tile queue head
+    uint32_t* min_keys;      // device, [batch]: ~key of the utterance's smallest log10 value (tcgen05 variant: decides
+                             // whether the dynamic-range clamp touches the utterance at all)
     int global_max;
     int fused_norm;          // the last CTA to finish an utterance normalises it in place
     int n_rows;              // rows of the mel partial-sum tile (DeviceTables::n_rows)

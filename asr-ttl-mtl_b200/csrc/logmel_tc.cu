@@ -24,10 +24,12 @@
 //     warps           max(x, g - 8), (x + 4) / 4 in place while the utterance's 0.96 MB is still L2-resident, so the
 //                     front-end is one launch whose DRAM traffic is the algorithmic read + write.
 // (One max over the whole call, or very long utterances: the shared pass-2 kernel normalises instead.)
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "kernels.h"
 #include "tc_core.cuh"
@@ -36,7 +38,7 @@ namespace b200mel {
 
 namespace {
 
-constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpNorm = 17;   // normalisers: warps 17..19
+constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpLoad = 17, kWarpNorm = 18;   // normalisers: warps 18, 19
 constexpr int kTcWarps = 20;
 constexpr int kTcThreads = kTcWarps * 32;   // 640
 constexpr uint32_t kSpinLimit = 1u << 17;    // x 20 us hint = 2.6 s: a protocol bug traps instead of hanging the device
@@ -44,10 +46,13 @@ constexpr uint32_t kWaitHintNs = 20000;      // suspend-time hint of one try_wai
 
 // Bring-up timeline (B200MEL_TC_TRACE=1): CTA 0 stamps clock64() at the hand-over points of its first tiles.
 constexpr int kTraceTiles = 8, kTraceEvents = 16, kTraceRoles = 6;
+constexpr int kStampCtas = 256, kTileStamps = 64;   // (x 2: fold start and epilogue end of every tile)
+#define TC_TILE_STAMPS (2 * kTileStamps + 32 + kStampCtas) //   // per-CTA start / end stamps, CTA 0's start of every tile
 #define TC_TRACE(role, tile_index, event)                                                                        \
     do {                                                                                                         \
-        if (trace != nullptr && blockIdx.x == 0 && (tile_index) < kTraceTiles && (threadIdx.x & 31) == 0)        \
-            trace[((role) * kTraceTiles + (tile_index)) * kTraceEvents + (event)] = clock64();                  \
+        if (trace != nullptr && blockIdx.x == 0 && (tile_index) >= trace_first && (tile_index) < trace_first + kTraceTiles &&      \
+            (threadIdx.x & 31) == 0)                                                                             \
+            trace[((role) * kTraceTiles + (tile_index) - trace_first) * kTraceEvents + (event)] = clock64();    \
     } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -214,44 +219,45 @@ struct TcBarriers {
 // In-place dynamic-range clamp + affine map (audio.py:155-156) of ONE TILE of a finished utterance: the rows this
 // CTA's epilogue wrote a few tile periods ago, read back through L2.  Every CTA normalises its own tiles, so the work
 // is spread exactly like the tiles are; nothing is queued.
-constexpr int kNormThreadsTc = 96;
 
-__device__ __forceinline__ float4 normalise4(float4 x, float g) {
-    x.x = normalise(x.x, g); x.y = normalise(x.y, g); x.z = normalise(x.z, g); x.w = normalise(x.w, g);
+// clamp of an already rescaled value y = (lg + 4) / 4 at floor_y = ((g - 8) + 4) / 4 (NaN when the max is NaN, as in
+// torch): identical to (max(lg, g - 8) + 4) / 4 because the rescaling is monotone
+__device__ __forceinline__ float clamp_scaled(float y, float floor_y) { return (floor_y != floor_y) ? floor_y : (y < floor_y ? floor_y : y); }
+__device__ __forceinline__ float4 normalise4(float4 x, float f) {
+    x.x = clamp_scaled(x.x, f); x.y = clamp_scaled(x.y, f); x.z = clamp_scaled(x.z, f); x.w = clamp_scaled(x.w, f);
     return x;
 }
 
+// one warp clamps one tile (NM rows of `frames` values at `pitch`) in place
 template <int NM>
-__device__ __forceinline__ void normalise_tile_tc(float* __restrict__ tile_out, int64_t pitch, int frames, float g, int nt) {
-    const int w = nt >> 5, lane = nt & 31;
+__device__ __forceinline__ void normalise_tile_tc(float* __restrict__ tile_out, int64_t pitch, int frames, float g /* the clamp in rescaled units */, int lane) {
     if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & 15u) == 0) {
-        // a warp takes whole mel rows (lane = float4 column, 512 contiguous bytes), four rows in flight
+        // whole mel rows (lane = float4 column, 512 contiguous bytes), four rows in flight
         if (lane < (frames >> 2)) {
-            float* p = tile_out + w * pitch + 4 * lane;
-            const int64_t step = 3 * pitch;
-            int row = w;
+            float* p = tile_out + 4 * lane;
+            int row = 0;
 #pragma unroll 1
-            for (; row + 9 < NM; row += 12, p += 4 * step) {
-                float4 x0 = __ldcg(reinterpret_cast<float4*>(p)), x1 = __ldcg(reinterpret_cast<float4*>(p + step));
-                float4 x2 = __ldcg(reinterpret_cast<float4*>(p + 2 * step)), x3 = __ldcg(reinterpret_cast<float4*>(p + 3 * step));
+            for (; row + 3 < NM; row += 4, p += 4 * pitch) {
+                float4 x0 = __ldcg(reinterpret_cast<float4*>(p)), x1 = __ldcg(reinterpret_cast<float4*>(p + pitch));
+                float4 x2 = __ldcg(reinterpret_cast<float4*>(p + 2 * pitch)), x3 = __ldcg(reinterpret_cast<float4*>(p + 3 * pitch));
                 *reinterpret_cast<float4*>(p) = normalise4(x0, g);
-                *reinterpret_cast<float4*>(p + step) = normalise4(x1, g);
-                *reinterpret_cast<float4*>(p + 2 * step) = normalise4(x2, g);
-                *reinterpret_cast<float4*>(p + 3 * step) = normalise4(x3, g);
+                *reinterpret_cast<float4*>(p + pitch) = normalise4(x1, g);
+                *reinterpret_cast<float4*>(p + 2 * pitch) = normalise4(x2, g);
+                *reinterpret_cast<float4*>(p + 3 * pitch) = normalise4(x3, g);
             }
 #pragma unroll 1
-            for (; row < NM; row += 3, p += step) *reinterpret_cast<float4*>(p) = normalise4(__ldcg(reinterpret_cast<float4*>(p)), g);
+            for (; row < NM; ++row, p += pitch) *reinterpret_cast<float4*>(p) = normalise4(__ldcg(reinterpret_cast<float4*>(p)), g);
         }
         const int rest = frames & 3;                                           // 0 for whole clips (pitch % 4 == 0)
         if (rest != 0)
-            for (int i = nt; i < NM * rest; i += kNormThreadsTc) {
+            for (int i = lane; i < NM * rest; i += 32) {
                 float* q = tile_out + (i / rest) * pitch + (frames & ~3) + i % rest;
-                *q = normalise(__ldcg(q), g);
+                *q = clamp_scaled(__ldcg(q), g);
             }
     } else {
-        for (int i = nt; i < NM * frames; i += kNormThreadsTc) {
+        for (int i = lane; i < NM * frames; i += 32) {
             float* q = tile_out + (i / frames) * pitch + i % frames;
-            *q = normalise(__ldcg(q), g);
+            *q = clamp_scaled(__ldcg(q), g);
         }
     }
 }
@@ -269,19 +275,34 @@ __device__ __forceinline__ TileCoord tile_coord(int64_t tile, int tiles_per_clip
 }
 
 // ---- loaders: one tile of audio into shared memory -----------------------------------------------
-// The 256 fold threads (which would otherwise idle until the tile is there) move
-// the tile as 5200 16-byte chunks (130 rows x 40) with cp.async (LDGSTS, L1 bypass) - many threads because the
-// copy rate is set by how many requests are in flight.  The source is one contiguous span, the destination rows
-// sit at pitch 164 words.  A chunk that touches a clip edge (reflect padding, zero tail, `lengths`), an unaligned
-// row or int16 PCM is written by hand.  Completion: every thread's copies arrive on `full` through
-// cp.async.mbarrier.arrive.noinc, its plain stores through a normal (release) arrive - the barrier expects
-// 2 x 256 arrivals per tile.
+// The tile is 130 rows of 160 samples (one contiguous span of the utterance) at pitch 164 words.
+//   TMA mode (fp32, 16-byte aligned rows, tile wholly inside the utterance): ONE tensor copy per tile.  The batch is
+//     described to the TMA unit as a 4-D tensor {164 samples, 4 quarter rows of 40, rows of 160, utterance} whose
+//     innermost extent (164) overlaps the next row on purpose: a {164, 1, 130, 1} box then lands in shared memory as
+//     130 rows at pitch 164 words - the padded, bank-conflict-free layout the fold reads - in a single instruction
+//     that completes on the `full` mbarrier by byte count (the 4 pad words are never read);
+//   cooperative mode (tiles at a clip edge - reflect padding, zero tail, `lengths` -, int16 PCM, unaligned rows): the
+//     256 fold threads, which would idle until the tile is there anyway, move it as 16-byte cp.async chunks / converted
+//     samples.
+// Either way `full` takes 9 arrivals per tile: lane 0 of the loader warp (with the expected byte count) and lane 0 of
+// each fold warp (at once in TMA mode, after its share of the copy in cooperative mode).
 constexpr int kProducerThreads = 256;
 constexpr int kChunksPerRow = kHop / 4;                       // 40
 constexpr int kTileChunks = kTcAudioRows * kChunksPerRow;     // 5200
+constexpr uint32_t kTmaTileBytes = kTcAudioWords * 4;         // 85280: the whole box, pad words included
+constexpr int kTmaLeadRows = 2, kTmaQuarter = 3;              // tile start = 160 t0 - 200 = 160 (t0 - 2) + 3 * 40
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+
+__device__ __forceinline__ int64_t valid_samples(const LogmelArgs& a, int64_t clip) {
+    int64_t valid = a.n_samples;
+    if (a.lengths != nullptr) {
+        const int64_t len = a.lengths[clip];
+        valid = len < 0 ? 0 : (len < valid ? len : valid);
+    }
+    return valid;
 }
 
 // Asks L2 for a later tile's samples (one bulk prefetch per tile, interior tiles only): the CTAs of a wave load in
@@ -298,75 +319,81 @@ __device__ __forceinline__ void prefetch_tile_l2(const LogmelArgs& a, const Tile
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(begin), "r"(static_cast<uint32_t>(end - begin)) : "memory");
 }
 
+// whether the TMA unit brings this tile (same answer in the loader warp and in the fold warps)
+template <typename InT>
+__device__ __forceinline__ bool tile_uses_tma(const LogmelArgs& a, int tma_rows, const TileCoord& tc) {
+    if constexpr (sizeof(InT) != 4) return false;
+    if (tma_rows <= 0 || tc.t0 < kTmaLeadRows || tc.t0 - kTmaLeadRows + kTcAudioRows > tma_rows) return false;
+    return static_cast<int64_t>(tc.t0) * kHop - kHalfWin + kTcAudioSamples <= valid_samples(a, tc.clip);
+}
+__device__ __forceinline__ void tma_load_tile(const CUtensorMap* map, const TileCoord& tc, float* s_audio, uint64_t* full) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(full)), "r"(kTmaTileBytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(s_audio)), "l"(map), "r"(0), "r"(kTmaQuarter), "r"(tc.t0 - kTmaLeadRows), "r"(static_cast<int>(tc.clip)),
+                   "r"(smem_u32(full)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_tile(const CUtensorMap* map, const TileCoord& tc) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(0), "r"(kTmaQuarter), "r"(tc.t0 - kTmaLeadRows), "r"(static_cast<int>(tc.clip)) : "memory");
+}
+
+// cooperative mode, the 256 fold threads
 template <typename InT>
 __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoord& tc, float* s_audio, uint64_t* full, int pt) {
     const InT* __restrict__ row = static_cast<const InT*>(a.audio) + tc.clip * a.stride_b;
-    int64_t valid = a.n_samples;
-    if (a.lengths != nullptr) {
-        const int64_t len = a.lengths[tc.clip];
-        valid = len < 0 ? 0 : (len < valid ? len : valid);
-    }
+    const int64_t valid = valid_samples(a, tc.clip);
     const int64_t s0 = static_cast<int64_t>(tc.t0) * kHop - kHalfWin;
     const bool aligned = sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
-    const uint32_t dst0 = smem_u32(s_audio);
     // chunk c = 40 r + k covers samples s0 + 4c .. + 3 and lands at word 164 r + 4 k
     int r = pt / kChunksPerRow, k = pt - r * kChunksPerRow;
-    if (aligned && s0 >= 0 && s0 + kTcAudioRows * kHop <= valid) {
-        const float* src = reinterpret_cast<const float*>(row) + s0 + 4 * pt;
-#pragma unroll 4
-        for (int c = pt; c < kTileChunks; c += kProducerThreads) {
-            cp_async16(dst0 + 4u * static_cast<uint32_t>(r * kTcRowPitch + 4 * k), src);
-            src += 4 * kProducerThreads;
-            r += 6; k += 16;                                   // 256 = 6 x 40 + 16
-            if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
-        }
-    } else {
-        for (int c = pt; c < kTileChunks; c += kProducerThreads) {
-            const int64_t pos = s0 + 4 * static_cast<int64_t>(c);
-            if (pos < s0 + kTcAudioSamples) {                  // the second half of row 129 is never read
-                float* dst = s_audio + r * kTcRowPitch + 4 * k;
-                if (aligned && pos >= 0 && pos + 4 <= valid) {
-                    cp_async16(smem_u32(dst), reinterpret_cast<const float*>(row) + pos);
-                } else {
+    for (int c = pt; c < kTileChunks; c += kProducerThreads) {
+        const int64_t pos = s0 + 4 * static_cast<int64_t>(c);
+        if (pos < s0 + kTcAudioSamples) {                  // the second half of row 129 is never read
+            float* dst = s_audio + r * kTcRowPitch + 4 * k;
+            if (aligned && pos >= 0 && pos + 4 <= valid) {
+                cp_async16(smem_u32(dst), reinterpret_cast<const float*>(row) + pos);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float v = 0.f;
-                        if (pos + i < a.total + kHalfWin) {
-                            const int64_t idx = reflect_source_index(pos + i, a.total);
-                            if (idx >= 0 && idx < valid) v = sample_to_float<InT>(__ldg(row + idx));
-                        }
-                        dst[i] = v;
+                for (int i = 0; i < 4; ++i) {
+                    float v = 0.f;
+                    if (pos + i < a.total + kHalfWin) {
+                        const int64_t idx = reflect_source_index(pos + i, a.total);
+                        if (idx >= 0 && idx < valid) v = sample_to_float<InT>(__ldg(row + idx));
                     }
+                    dst[i] = v;
                 }
             }
-            r += 6; k += 16;
-            if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
         }
+        r += 6; k += 16;                                   // 256 = 6 x 40 + 16
+        if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
     }
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full)) : "memory");
-    mbar_arrive(full);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if ((pt & 31) == 0) mbar_arrive(full);
 }
 
 // ---- fold warps: one sweep of one tile, A operand -> tensor memory -----------------------------------
-__constant__ TcFoldTable c_fold = tc_make_fold_table();
+__constant__ TcFoldRows c_fold_rows = tc_make_fold_rows();
 
-// A compact 12-iteration loop per sweep (not 13 unrolled chunks): the fold code stays resident in the instruction
-// caches, and the table rows are read with warp-uniform constant loads.
-template <int SWEEP>
-__device__ __forceinline__ void sweep_store(const float* fr, uint32_t lane_addr) {
-    const TcFoldChunk* __restrict__ table = c_fold.c[SWEEP];
-    const uint32_t u1 = lane_addr + tc_hi_col(2 * SWEEP);          // hi block of the sweep's first unit (0 or 2)
+// One compact loop for both sweeps (see TcFoldRows): 12 main chunks, then the leftover chunk with its own store
+// pattern.  `sweep` is warp-uniform, so the table rows arrive through the uniform datapath.
+__device__ __forceinline__ void sweep_store(int sweep, const float* fr, uint32_t lane_addr) {
+    const TcFoldRow* __restrict__ rows = c_fold_rows.row[sweep];
+    const float sign = c_fold_rows.sign[sweep];
+    float head[2];
+    head[0] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(fr) + c_fold_rows.head[sweep][0]);
+    head[1] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(fr) + c_fold_rows.head[sweep][1]);
+    uint32_t c = lane_addr + (sweep == 0 ? tc_hi_col(0) : tc_hi_col(2));   // hi block of the sweep's first unit
     uint32_t hf[4], lf[4], hs[4], ls[4];
-#pragma unroll 2
-    for (int j = 0; j < 2 * kTcMainSteps; ++j) {                   // slots 8j..8j+7 of the main blocks
-        tc_sweep_chunk<SWEEP>(fr, table[j], hf, lf, hs, ls);
-        const uint32_t c = u1 + 4 * j;
-        tmem_st4(c, hf); tmem_st4(c + 48, lf);                     // unit: [hi 48 | lo 48], next unit 96 columns on
+#pragma unroll 1
+    for (int j = 0; j < 2 * kTcMainSteps; ++j, c += 4) {                   // slots 8j..8j+7 of the main blocks
+        tc_sweep_chunk_row(fr, rows[j], sign, head, hf, lf, hs, ls);
+        tmem_st4(c, hf); tmem_st4(c + 48, lf);                             // unit: [hi 48 | lo 48], next unit 96 columns on
         tmem_st4(c + 96, hs); tmem_st4(c + 144, ls);
     }
-    tc_sweep_chunk<SWEEP>(fr, table[2 * kTcMainSteps], hf, lf, hs, ls);
+    tc_sweep_chunk_row(fr, rows[2 * kTcMainSteps], sign, head, hf, lf, hs, ls);
     // slots 96..101: [hi x 3 | lo x 3] columns of the leftover area, second unit 6 columns on
-    const uint32_t b1 = lane_addr + tc_left_col(2 * SWEEP), b2 = b1 + 6;
+    const uint32_t b1 = lane_addr + (sweep == 0 ? tc_left_col(0) : tc_left_col(2)), b2 = b1 + 6;
     tmem_st2(b1, hf[0], hf[1]); tmem_st2(b1 + 2, hf[2], lf[0]); tmem_st2(b1 + 4, lf[1], lf[2]);
     tmem_st2(b2, hs[0], hs[1]); tmem_st2(b2 + 2, hs[2], ls[0]); tmem_st2(b2 + 4, ls[1], ls[2]);
 }
@@ -376,7 +403,7 @@ static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) =
 // ---- epilogue helpers -----------------------------------------------------------------------------
 template <int NM, int HALF>
 __device__ __forceinline__ void epilogue_unit(int unit, uint32_t d_addr, uint64_t* d_full, uint64_t* d_empty, uint32_t parity,
-                                              int lane, float (&acc)[TcEpilogueLayout<NM>::acc_size(HALF)], long long* trace, int ti, int quad) {
+                                              int lane, float (&acc)[TcEpilogueLayout<NM>::acc_size(HALF)], long long* trace, const int trace_first, int ti, int quad) {
     using L = TcEpilogueLayout<NM>;
     float d[L::cols(HALF)];
     mbar_wait(d_full, parity);
@@ -396,7 +423,7 @@ __device__ __forceinline__ void epilogue_unit(int unit, uint32_t d_addr, uint64_
 }
 
 template <int NM, int HALF>
-__device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, long long* trace, TcBarriers* bars,
+__device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, long long* trace, const int trace_first, TcBarriers* bars,
                                               float* s_straddle,
                                               uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
     using L = TcEpilogueLayout<NM>;
@@ -413,7 +440,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
 #pragma unroll 1
         for (int u = 0; u < kTcUnits; ++u) {
             if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u);
-            epilogue_unit<NM, HALF>(debug_stage == 4 ? -1 : u, d_addr, &bars->d_full, &bars->d_empty, d_parity, lane, acc, trace, ti, quad);
+            epilogue_unit<NM, HALF>(debug_stage == 4 ? -1 : u, d_addr, &bars->d_full, &bars->d_empty, d_parity, lane, acc, trace, trace_first, ti, quad);
             if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
             d_parity ^= 1u;
         }
@@ -435,14 +462,19 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
         constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
         const int64_t pitch = a.n_frames;
         float* out = a.out + (tc.clip * NM + m_begin) * pitch + t;
-        float mx = __uint_as_float(0xff800000u);
+        // With the normalisation fused, the affine half of it, (x + 4) / 4, is applied here (one FFMA, the same single
+        // rounding as audio.py:156) and only the clamp at max - 8 is left for the normaliser warps - which skip the
+        // utterance when its smallest value is not below max - 8 (tracked here as well).
+        float mx = __uint_as_float(0xff800000u), mn = __uint_as_float(0x7f800000u);
         if (live) {
+            const float scale = a.fused_norm ? 0.25f : 1.0f, shift = a.fused_norm ? 1.0f : 0.0f;
 #pragma unroll
             for (int m = m_begin; m < m_end; ++m) {
                 const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
-                *out = lg;
+                *out = fmaf(lg, scale, shift);
                 out += pitch;
                 mx = max_nan(mx, lg);
+                mn = fminf(mn, lg);
             }
         }
 #pragma unroll
@@ -451,6 +483,9 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
         key = __reduce_max_sync(0xffffffffu, key);
         if (lane == 0) atomicMax(a.max_keys + (a.global_max ? 0 : tc.clip), key);
         if (a.fused_norm) {
+            uint32_t inv = live ? ~max_key_encode(mn) : 0u;
+            inv = __reduce_max_sync(0xffffffffu, inv);
+            if (lane == 0) atomicMax(a.min_keys + tc.clip, inv);
             // count this warp's share of the utterance: the normaliser warps of every CTA that holds one of its tiles
             // wait for the count to be complete (8 epilogue warps per tile)
             __threadfence();   // this tile's rows and max are visible before they are counted
@@ -458,20 +493,33 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
             if (lane == 0) atomicAdd(a.done_counters + tc.clip, 1u);
         }
         if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
+        if (HALF == 0 && trace != nullptr && blockIdx.x == 0 && quad == 0 && lane == 0 && ti < kTileStamps)
+            trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + kTileStamps + ti] = clock64();
     }
 }
 
 template <typename InT, int NM>
 __global__ void __launch_bounds__(kTcThreads, 1)
-logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __restrict__ operands, const int debug_stage,
-                 long long* __restrict__ trace) {
+logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ CUtensorMap audio_map, const int tma_rows,
+                 const unsigned char* __restrict__ operands, const int debug_stage, long long* __restrict__ trace, const int trace_first) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_audio = reinterpret_cast<float*>(smem_raw + kSmemAudio);
     float* s_straddle = reinterpret_cast<float*>(smem_raw + kSmemStraddle);
     __shared__ __align__(8) TcBarriers bars;
     __shared__ uint32_t s_tmem;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from
+    // it (role, TMEM lane quadrant, column addresses) in uniform registers
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31, quad = warp & 3;
+    if (trace != nullptr && tid == 0) {   // bring-up: every CTA stamps its start and end (cycles and nanoseconds)
+        long long* stamp = trace + kTraceRoles * kTraceTiles * kTraceEvents + 6 * blockIdx.x;
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        stamp[0] = clock64(); stamp[1] = static_cast<long long>(ns);
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + 2 * kTileStamps + 32 + blockIdx.x] = smid;
+    }
     const int tiles_per_clip = (a.n_frames + kTcTileFrames - 1) / kTcTileFrames;
     int64_t total_tiles = a.batch * tiles_per_clip;
     // bring-up aid (B200MEL_TC_DEBUG): 1 = setup only, 2 = + producer and folds of ONE tile,
@@ -485,7 +533,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        mbar_init(&bars.audio_full, 2 * kProducerThreads);
+        mbar_init(&bars.audio_full, 9);
         mbar_init(&bars.audio_empty, 8);
         mbar_init(&bars.a_full[0], 4); mbar_init(&bars.a_full[1], 4);
         mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
@@ -518,7 +566,6 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
     // (a setmaxnreg.inc can only take what another warpgroup released): folds 80 + 80, epilogue 144 + 144, rest 32
     if (warp < kWarpEpi0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        if (tid == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) prefetch_tile_l2<InT>(a, tile_coord(blockIdx.x, tiles_per_clip));
         // ===== fold warps: E sweep (warps 0-3) / O sweep (warps 4-7) =====
         const int sweep = warp < kWarpO ? 0 : 1;
         const float* fr = s_audio + (quad * 32 + lane) * kTcRowPitch;
@@ -526,16 +573,21 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
         int ti = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
             if (quad == 0) TC_TRACE(1 + sweep, ti, 0);
-            // while waiting for the buffer, pull the NEXT tile towards L2 (this one was asked for a tile ago)
-            if (tid == 0 && tile + gridDim.x < total_tiles) prefetch_tile_l2<InT>(a, tile_coord(tile + gridDim.x, tiles_per_clip));
-            mbar_wait(&bars.audio_empty, parity ^ 1u);      // every fold warp has finished reading the previous tile
-            produce_tile<InT>(a, tile_coord(tile, tiles_per_clip), s_audio, &bars.audio_full, tid);
+            if (trace != nullptr && blockIdx.x == 0 && tid == 0 && ti < kTileStamps)
+                trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + ti] = clock64();
+            const TileCoord tcl = tile_coord(tile, tiles_per_clip);
+            if (tile_uses_tma<InT>(a, tma_rows, tcl)) {
+                if (lane == 0) mbar_arrive(&bars.audio_full);   // the loader warp brings this tile
+            } else {
+                mbar_wait(&bars.audio_empty, parity ^ 1u);      // every fold warp has finished reading the previous tile
+                produce_tile<InT>(a, tcl, s_audio, &bars.audio_full, tid);
+            }
             mbar_wait(&bars.audio_full, parity);
             if (quad == 0) TC_TRACE(1 + sweep, ti, 1);
             mbar_wait(&bars.a_empty[sweep], parity ^ 1u);   // the tensor cores are done with the previous tile's operand
             if (quad == 0) TC_TRACE(1 + sweep, ti, 2);
             tc_fence_after();
-            if (sweep == 0) sweep_store<0>(fr, lane_addr); else sweep_store<1>(fr, lane_addr);
+            sweep_store(sweep, fr, lane_addr);
             if (quad == 0) TC_TRACE(1 + sweep, ti, 3);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
@@ -548,8 +600,8 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
         // ===== epilogue warps =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         if (debug_stage > 0 && debug_stage < 4) total_tiles = 0;
-        if (warp < kWarpEpi1) epilogue_role<NM, 0>(a, debug_stage, trace, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
-        else epilogue_role<NM, 1>(a, debug_stage, trace, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        if (warp < kWarpEpi1) epilogue_role<NM, 0>(a, debug_stage, trace, trace_first, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        else epilogue_role<NM, 1>(a, debug_stage, trace, trace_first, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == kWarpMma && (debug_stage == 0 || debug_stage >= 3)) {
@@ -583,35 +635,88 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const unsigned char* __re
                 a_parity ^= 1u;
             }
             if (debug_stage == 3 && total_tiles > 0) mbar_wait(&bars.d_full, 1);   // nobody drains the accumulator in this stage
-        } else if (warp >= kWarpNorm && a.fused_norm && debug_stage == 0) {
-            // ===== normaliser warps =====
-            // Walk this CTA's tiles a little behind the epilogue: once every tile of the utterance has been counted its
-            // max is final, and this CTA's own tile (still in L2) is clamped and rescaled in place.
-            const int nt = tid - kWarpNorm * 32;
-            const unsigned need = 8u * static_cast<unsigned>(tiles_per_clip);
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord tc = tile_coord(tile, tiles_per_clip);
+        } else if (warp == kWarpLoad) {
+            // ===== loader warp =====
+            // Ask L2 for a tile one tile period before it is copied: the CTAs of a wave load in lock-step, so without
+            // the prefetch every staging phase waits on an HBM burst while HBM idles the rest of the time.
+            auto prefetch = [&](int64_t tile) {
+                const TileCoord tp = tile_coord(tile, tiles_per_clip);
+                if (tile_uses_tma<InT>(a, tma_rows, tp)) tma_prefetch_tile(&audio_map, tp);
+                else prefetch_tile_l2<InT>(a, tp);
+            };
+            if (lane == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) prefetch(blockIdx.x);
+            uint32_t parity = 1;   // audio_empty: the first wait passes
+            int ti = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                TC_TRACE(0, ti, 0);
+                if (lane == 0 && tile + gridDim.x < total_tiles) prefetch(tile + gridDim.x);
+                const TileCoord tcl = tile_coord(tile, tiles_per_clip);
+                const bool tma = tile_uses_tma<InT>(a, tma_rows, tcl);
+                mbar_wait(&bars.audio_empty, parity);           // every fold warp has finished reading the previous tile
+                parity ^= 1u;
+                TC_TRACE(0, ti, 1);
                 if (lane == 0) {
+                    if (tma) tma_load_tile(&audio_map, tcl, s_audio, &bars.audio_full);
+                    else mbar_arrive(&bars.audio_full);         // cooperative mode: the fold warps bring the tile
+                }
+                TC_TRACE(0, ti, 2);
+            }
+        } else if (warp >= kWarpNorm && a.fused_norm && debug_stage == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) {
+            // ===== normaliser warps =====
+            // The two warps take this CTA's tiles in alternating groups of 32, one tile per lane: a lane waits until
+            // every tile of its utterance has been counted (the max is final then), and decides from the utterance's
+            // extremes whether the clamp at max - 8 touches it at all; tiles that need it (digital silence, zero
+            // padding) are clamped in place by the whole warp while they are still in L2.
+            const unsigned need = 8u * static_cast<unsigned>(tiles_per_clip);
+            const int64_t my_tiles = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+            for (int64_t g0 = 32 * (warp - kWarpNorm); g0 < my_tiles; g0 += 64) {
+                const bool have = g0 + lane < my_tiles;
+                const TileCoord tc = tile_coord(blockIdx.x + (have ? g0 + lane : 0) * gridDim.x, tiles_per_clip);
+                if (have) {
+                    const volatile uint32_t* counter = a.done_counters + tc.clip;
                     uint32_t polls = 0;
-                    while (true) {
-                        unsigned seen;
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.done_counters + tc.clip) : "memory");
-                        if (seen >= need) break;
-                        if (++polls > (1u << 22)) tc_fault(0x2000000u | (static_cast<uint32_t>(tile) << 8 & 0xffff00u) | (threadIdx.x >> 5));
-                        __nanosleep(500);
+                    while (*counter < need) {
+                        if (++polls > (1u << 21)) tc_fault(0x2000000u | (static_cast<uint32_t>(g0 + lane) << 8 & 0xffff00u) | (threadIdx.x >> 5));
+                        __nanosleep(1000);
                     }
                 }
                 __syncwarp();
-                const float g = max_key_decode(__ldcg(a.max_keys + tc.clip));
-                const int frames = a.n_frames - tc.t0 < kTcTileFrames ? a.n_frames - tc.t0 : kTcTileFrames;
-                normalise_tile_tc<NM>(a.out + tc.clip * NM * static_cast<int64_t>(a.n_frames) + tc.t0, a.n_frames, frames, g, nt);
+                __threadfence();   // the extremes (and the rows) are read after the counts
+                float g = 0.f;
+                bool fix = false;
+                if (have) {
+                    g = max_key_decode(__ldcg(a.max_keys + tc.clip));
+                    const float smallest = max_key_decode(~__ldcg(a.min_keys + tc.clip));
+                    fix = !(smallest >= g - 8.0f);    // nothing below the clamp: leave the utterance alone (false for a NaN max)
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, fix);
+                while (todo != 0) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int64_t clip = __shfl_sync(0xffffffffu, static_cast<int>(tc.clip), src);
+                    const int t0 = __shfl_sync(0xffffffffu, tc.t0, src);
+                    const float gs = __shfl_sync(0xffffffffu, g, src);
+                    const int frames = a.n_frames - t0 < kTcTileFrames ? a.n_frames - t0 : kTcTileFrames;
+                    const float floor_y = ((gs - 8.0f) + 4.0f) * 0.25f;
+                    normalise_tile_tc<NM>(a.out + clip * NM * static_cast<int64_t>(a.n_frames) + t0, a.n_frames, frames, floor_y, lane);
+                }
             }
         }
         __syncwarp();
     }
 
+    if (trace != nullptr && lane == 0 && (warp == kWarpEpi0 || warp == kTcWarps - 1))   // pipeline / normaliser done, every CTA
+        trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * blockIdx.x + (warp == kWarpEpi0 ? 4 : 5)] = clock64();
+    if (trace != nullptr && blockIdx.x == 0 && lane == 0)   // when each warp of CTA 0 reaches the final barrier
+        trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + 2 * kTileStamps + warp] = clock64();
     tc_fence_before();
     __syncthreads();
+    if (trace != nullptr && tid == 0) {
+        long long* stamp = trace + kTraceRoles * kTraceTiles * kTraceEvents + 6 * blockIdx.x;
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        stamp[2] = clock64(); stamp[3] = static_cast<long long>(ns);
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
@@ -646,26 +751,107 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
                 std::fprintf(stderr, "b200mel tcgen05 kernel: wait timed out, code 0x%08x in CTA %u\n", fault_report[0], fault_report[1]);
         });
     }
+    // the batch as the TMA unit sees it (see "loaders" above); any reason it cannot be described leaves tma_rows = 0
+    // and every tile in cooperative mode
+    CUtensorMap audio_map;
+    std::memset(&audio_map, 0, sizeof(audio_map));
+    int tma_rows = 0;
+    if (sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(a.audio) & 15u) == 0 && a.stride_b % 4 == 0 && a.n_samples >= 284 + kHop &&
+        a.batch < (int64_t{1} << 31)) {
+        using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = [] {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+            return reinterpret_cast<EncodeFn>(fn);
+        }();
+        // rows r with 160 r + 3 * 40 + 164 <= n_samples: every element of such a row lies inside the utterance's memory
+        const int64_t rows = (a.n_samples - 284) / kHop + 1;
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kTcRowPitch), 4, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(a.batch)};
+        const cuuint64_t strides[3] = {kHop, kHop * 4, static_cast<cuuint64_t>(a.stride_b) * 4};   // bytes, dims 1..3
+        const cuuint32_t box[4] = {static_cast<cuuint32_t>(kTcRowPitch), 1, static_cast<cuuint32_t>(kTcAudioRows), 1};
+        const cuuint32_t elem[4] = {1, 1, 1, 1};
+        if (encode != nullptr && rows < (int64_t{1} << 31) &&
+            encode(&audio_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(a.audio), dims, strides, box, elem,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            tma_rows = static_cast<int>(rows);
+    }
+    static const bool no_tma = std::getenv("B200MEL_TC_NO_TMA") != nullptr;   // bring-up: force cooperative loading
+    if (no_tma) tma_rows = 0;
+    static const bool say_tma = std::getenv("B200MEL_TC_VERBOSE") != nullptr;
+    if (say_tma) std::fprintf(stderr, "b200mel tcgen05: tma_rows = %d\n", tma_rows);
     ProfileScope profile(2, stream);
     static const int debug_stage = std::getenv("B200MEL_TC_DEBUG") ? std::atoi(std::getenv("B200MEL_TC_DEBUG")) : 0;
     static long long* trace = nullptr;
-    static const bool want_trace = std::getenv("B200MEL_TC_TRACE") != nullptr;
-    constexpr size_t kTraceBytes = sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents;
+    static const bool want_trace = std::getenv("B200MEL_TC_TRACE") != nullptr;   // value: first of the 8 traced tiles of CTA 0
+    static const int trace_first = want_trace ? std::atoi(std::getenv("B200MEL_TC_TRACE")) : 0;
+    constexpr int kTraceWords = kTraceRoles * kTraceTiles * kTraceEvents;
+    constexpr size_t kTraceBytes = sizeof(long long) * (kTraceWords + 6 * kStampCtas + TC_TILE_STAMPS);
     if (want_trace && trace == nullptr) { cudaMalloc(&trace, kTraceBytes); }
     if (want_trace) cudaMemsetAsync(trace, 0, kTraceBytes, stream);
-    logmel_tc_kernel<InT, NM><<<grid, kTcThreads, kSmemBytes, stream>>>(a, tables->operands, debug_stage, want_trace ? trace : nullptr);
+    logmel_tc_kernel<InT, NM><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, debug_stage,
+                                                                          want_trace ? trace : nullptr, trace_first);
     count_launch();
     err = cudaGetLastError();
     if (want_trace && err == cudaSuccess) {   // bring-up only: synchronises and prints CTA 0's timeline
-        static long long host[kTraceRoles * kTraceTiles * kTraceEvents];
+        static long long host[kTraceWords + 6 * kStampCtas + TC_TILE_STAMPS];
         cudaStreamSynchronize(stream);
         cudaMemcpy(host, trace, kTraceBytes, cudaMemcpyDeviceToHost);
+        {
+            const long long* st = host + kTraceWords;
+            long long ns0 = 0, ns1 = 0, cyc_min = 0, cyc_max = 0; double cyc_sum = 0, mhz_sum = 0;
+            for (unsigned b = 0; b < grid && b < kStampCtas; ++b) {
+                const long long cyc = st[6 * b + 2] - st[6 * b], ns = st[6 * b + 3] - st[6 * b + 1];
+                if (b == 0 || st[6 * b + 1] < ns0) ns0 = st[6 * b + 1];
+                if (b == 0 || st[6 * b + 3] > ns1) ns1 = st[6 * b + 3];
+                if (b == 0 || cyc < cyc_min) cyc_min = cyc;
+                if (b == 0 || cyc > cyc_max) cyc_max = cyc;
+                cyc_sum += cyc; mhz_sum += ns > 0 ? 1e3 * cyc / ns : 0;
+            }
+            {
+                long long pmin = 0, pmax = 0; double psum = 0;
+                for (unsigned b = 0; b < grid && b < kStampCtas; ++b) {
+                    const long long pc = st[6 * b + 4] - st[6 * b];
+                    if (b == 0 || pc < pmin) pmin = pc;
+                    if (b == 0 || pc > pmax) pmax = pc;
+                    psum += pc;
+                }
+                std::fprintf(stderr, "trace CTAs: epilogue of the last tile done after min %lld avg %.0f max %lld cycles\n", pmin, psum / grid, pmax);
+                std::fprintf(stderr, "trace CTA pipeline k-cycles by SM id (sm:kcycles@MHz):");
+                const long long* sm = host + kTraceWords + 6 * kStampCtas + 2 * kTileStamps + 32;
+                for (unsigned want = 0; want < 160; ++want)
+                    for (unsigned b = 0; b < grid && b < kStampCtas; ++b)
+                        if (sm[b] == want) {
+                            const long long ns = st[6 * b + 3] - st[6 * b + 1];
+                            std::fprintf(stderr, " %u:%lld@%lld", want, (st[6 * b + 4] - st[6 * b]) / 1000, ns > 0 ? 1000 * (st[6 * b + 2] - st[6 * b]) / ns : 0);
+                        }
+                std::fprintf(stderr, "\n");
+            }
+            std::fprintf(stderr, "trace CTAs: span %lld ns, cycles min %lld avg %.0f max %lld, SM clock %.0f MHz, %.1f tiles per CTA\n",
+                         ns1 - ns0, cyc_min, cyc_sum / grid, cyc_max, mhz_sum / grid, static_cast<double>(tiles) / grid);
+        }
+        {
+            const long long* ts = host + kTraceWords + 6 * kStampCtas;
+            std::fprintf(stderr, "trace CTA 0 tile starts (cycles after the CTA's start; then deltas):");
+            for (int i = 0; i < kTileStamps && ts[i] != 0; ++i)
+                std::fprintf(stderr, " %lld", i == 0 ? ts[0] - host[kTraceWords] : ts[i] - ts[i - 1]);
+            std::fprintf(stderr, "  | end after last start: %lld\n", host[kTraceWords + 2] - ts[(tiles + grid - 1) / grid - 1]);
+            std::fprintf(stderr, "trace CTA 0 warps reach the final barrier at (k cycles):");
+            for (int w = 0; w < kTcWarps; ++w) std::fprintf(stderr, " %lld", (ts[2 * kTileStamps + w] - host[kTraceWords]) / 1000);
+            std::fprintf(stderr, "\n");
+            std::fprintf(stderr, "trace CTA 0 epilogue ends minus fold starts:");
+            for (int i = 0; i < kTileStamps && ts[i] != 0; ++i) std::fprintf(stderr, " %lld", ts[kTileStamps + i] - ts[i]);
+            std::fprintf(stderr, "\n");
+        }
         long long t0 = 0;
-        for (long long v : host) if (v != 0 && (t0 == 0 || v < t0)) t0 = v;
+        for (int i = 0; i < kTraceWords; ++i) { const long long v = host[i]; if (v != 0 && (t0 == 0 || v < t0)) t0 = v; }
         static const char* names[kTraceRoles] = {"producer", "fold-E", "fold-O", "mma", "epi-0", "epi-1"};
         for (int r = 0; r < kTraceRoles; ++r)
             for (int t = 0; t < kTraceTiles; ++t) {
-                std::fprintf(stderr, "trace %-8s tile %d:", names[r], t);
+                std::fprintf(stderr, "trace %-8s tile %d:", names[r], t + trace_first);
                 for (int e = 0; e < kTraceEvents; ++e) {
                     const long long v = host[(r * kTraceTiles + t) * kTraceEvents + e];
                     if (v) std::fprintf(stderr, " %d:%lld", e, v - t0);

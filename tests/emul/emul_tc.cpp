@@ -49,26 +49,53 @@ float unit_column(const TcTables& tab, const std::vector<uint32_t>& tmem, int f,
 }
 
 constexpr TcFoldTable kFold = tc_make_fold_table();
+constexpr TcFoldWeights kFoldWeights = tc_make_fold_weights();
+constexpr TcFoldRows kFoldRows = tc_make_fold_rows();
+float head_row[2][2];     // head carry of the row-driven form, per sweep
+int g_chunk_mismatch = 0;   // set when the compile-time chunk and the table-driven chunk disagree
 
 // one sweep of one frame, stored to the emulated tensor-memory lane exactly like the kernel's fold warps do
-void sweep_to_tmem(int sweep, const float* fr, uint32_t* lane) {
-    const int u1 = 2 * sweep, u2 = u1 + 1;
-    for (int j = 0; j < kTcChunks; ++j) {
-        uint32_t hf[4], lf[4], hs[4], ls[4];
-        if (sweep == 0) tc_sweep_chunk<0>(fr, kFold.c[0][j], hf, lf, hs, ls);
-        else tc_sweep_chunk<1>(fr, kFold.c[1][j], hf, lf, hs, ls);
-        if (j < 2 * kTcMainSteps) {
-            for (int q = 0; q < 4; ++q) {
-                lane[tc_hi_col(u1) + 4 * j + q] = hf[q]; lane[tc_lo_col(u1) + 4 * j + q] = lf[q];
-                lane[tc_hi_col(u2) + 4 * j + q] = hs[q]; lane[tc_lo_col(u2) + 4 * j + q] = ls[q];
-            }
-        } else {
-            for (int q = 0; q < 3; ++q) {
-                lane[tc_left_col(u1) + q] = hf[q]; lane[tc_left_col(u1) + 3 + q] = lf[q];
-                lane[tc_left_col(u2) + q] = hs[q]; lane[tc_left_col(u2) + 3 + q] = ls[q];
-            }
+template <int SWEEP, int J>
+void chunk_to_tmem(const float* fr, float (&head)[2], uint32_t* lane) {
+    constexpr int u1 = 2 * SWEEP, u2 = u1 + 1;
+    uint32_t hf[4], lf[4], hs[4], ls[4];
+    tc_sweep_chunk_ct<SWEEP, J>(fr, kFoldWeights, head, hf, lf, hs, ls);
+    {   // the table-driven form of the same chunk must agree bit for bit
+        uint32_t hf2[4], lf2[4], hs2[4], ls2[4];
+        tc_sweep_chunk<SWEEP>(fr, kFold.c[SWEEP][J], hf2, lf2, hs2, ls2);
+        const int live = J < 2 * kTcMainSteps ? 4 : 3;
+        for (int q = 0; q < live; ++q)
+            if (hf[q] != hf2[q] || lf[q] != lf2[q] || hs[q] != hs2[q] || ls[q] != ls2[q]) g_chunk_mismatch = 1;
+    }
+    {   // ... and so must the row-driven form the kernel runs (its own head carry, checked chunk by chunk)
+        if (J == 0) { head_row[SWEEP][0] = fr[kFoldRows.head[SWEEP][0] / 4]; head_row[SWEEP][1] = fr[kFoldRows.head[SWEEP][1] / 4]; }
+        uint32_t hf3[4], lf3[4], hs3[4], ls3[4];
+        tc_sweep_chunk_row(fr, kFoldRows.row[SWEEP][J], kFoldRows.sign[SWEEP], head_row[SWEEP], hf3, lf3, hs3, ls3);
+        const int live = J < 2 * kTcMainSteps ? 4 : 3;
+        for (int q = 0; q < live; ++q)
+            if (hf[q] != hf3[q] || lf[q] != lf3[q] || hs[q] != hs3[q] || ls[q] != ls3[q]) g_chunk_mismatch = 1;
+    }
+    if (J < 2 * kTcMainSteps) {
+        for (int q = 0; q < 4; ++q) {
+            lane[tc_hi_col(u1) + 4 * J + q] = hf[q]; lane[tc_lo_col(u1) + 4 * J + q] = lf[q];
+            lane[tc_hi_col(u2) + 4 * J + q] = hs[q]; lane[tc_lo_col(u2) + 4 * J + q] = ls[q];
+        }
+    } else {
+        for (int q = 0; q < 3; ++q) {
+            lane[tc_left_col(u1) + q] = hf[q]; lane[tc_left_col(u1) + 3 + q] = lf[q];
+            lane[tc_left_col(u2) + q] = hs[q]; lane[tc_left_col(u2) + 3 + q] = ls[q];
         }
     }
+}
+template <int SWEEP, int... J>
+void sweep_seq(const float* fr, uint32_t* lane, std::integer_sequence<int, J...>) {
+    float head[2];
+    tc_sweep_heads<SWEEP>(fr, head);
+    (chunk_to_tmem<SWEEP, J>(fr, head, lane), ...);
+}
+void sweep_to_tmem(int sweep, const float* fr, uint32_t* lane) {
+    if (sweep == 0) sweep_seq<0>(fr, lane, std::make_integer_sequence<int, kTcChunks>{});
+    else sweep_seq<1>(fr, lane, std::make_integer_sequence<int, kTcChunks>{});
 }
 
 template <int NM, int U>
@@ -179,3 +206,7 @@ extern "C" int emul_tc_frame_spectrum(const float* frame400, double* re, double*
     }
     return 0;
 }
+
+// 1 when any chunk computed so far differed between the compile-time form (what the kernel runs) and the
+// table-driven form of the fold (tc_core.cuh)
+extern "C" int emul_tc_chunk_mismatch() { return g_chunk_mismatch; }

@@ -46,6 +46,14 @@ def test_emulated_tc_variant_matches_golden_cases(emul_tc, golden):
         assert got.shape == tuple(c["shape"]) and err <= TOL, (c, err)
 
 
+def test_compile_time_fold_equals_table_driven_fold(emul_tc, golden):
+    """The unrolled chunk the kernel runs (tc_sweep_chunk_ct) and the table-driven one agree bit for bit."""
+    x = signals.make_signal("gauss", 16000, 5)
+    emul_tc.run(x, 80, golden["filters_80"])
+    emul_tc.run(signals.make_signal("chirp", 16000, 6), 128, golden["filters_128"])
+    assert emul_tc.emul_tc_chunk_mismatch() == 0
+
+
 @pytest.mark.parametrize("kind", ["chirp", "two_tone", "sine1k_noise"])
 def test_split_precision_stays_close_to_the_f64_spec(emul_tc, golden, kind):
     x = signals.make_signal(kind, 32000, 77)
