@@ -76,8 +76,7 @@ __device__ __noinline__ void tc_fault(uint32_t code) {
     }
     __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait_addr(const uint32_t addr, uint32_t parity) {
     uint32_t done = 0, spins = 0;
     while (true) {
         asm volatile(
@@ -90,6 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > kSpinLimit) tc_fault(0x1000000u | ((addr & 0xfffu) << 12) | (parity << 8) | (threadIdx.x >> 5));
     }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -174,33 +174,29 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\n@P tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 0;\n}\n"
                      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kTcIdesc) : "memory");
 }
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+__device__ __forceinline__ void mma_commit_addr(uint32_t bar_addr) {
     asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\n@P tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n"
-                 ::"r"(smem_u32(bar)) : "memory");
+                 ::"r"(bar_addr) : "memory");
 }
+__device__ __forceinline__ void mma_commit(uint64_t* bar) { mma_commit_addr(smem_u32(bar)); }
 
-// all tensor-core work of unit U for one tile: 6 K steps x (hi Bh, lo Bh, hi Bl) + the leftover step twice
-template <int U>
-__device__ __forceinline__ void mma_issue_unit(uint32_t tmem, uint32_t desc0) {
-    constexpr int m = tc_unit_matrix(U);
-    constexpr uint32_t kStep = (2 * kTcStripBytes) >> 4;   // K step s = strips 2s, 2s+1 = slots 16s..16s+15
-    const uint32_t d_tmem = tmem + kTcDCol;
-    const uint32_t a_hi = tmem + tc_hi_col(U), a_lo = tmem + tc_lo_col(U);
-    const uint32_t b_hi = desc0 + (tc_matrix_offset(m, 0) >> 4), b_lo = desc0 + (tc_matrix_offset(m, 1) >> 4);
-    mma_f16_ts<false>(d_tmem, a_hi, b_hi);
-    mma_f16_ts<true>(d_tmem, a_lo, b_hi);
-    mma_f16_ts<true>(d_tmem, a_hi, b_lo);
-#pragma unroll 1
-    for (uint32_t s = 1; s < kTcMainSteps; ++s) {
-        mma_f16_ts<true>(d_tmem, a_hi + 8 * s, b_hi + kStep * s);
-        mma_f16_ts<true>(d_tmem, a_lo + 8 * s, b_hi + kStep * s);
-        mma_f16_ts<true>(d_tmem, a_hi + 8 * s, b_lo + kStep * s);
+// what the issue loop needs per unit: operand columns and matrix offsets (descriptor units of 16 bytes); one tile's
+// tensor-core work for a unit is 6 K steps x (hi Bh, lo Bh, hi Bl) + the leftover step twice
+struct TcUnitIssue { uint32_t a_hi, a_lo, a_left, b_hi, b_lo, b_left0, b_left1, pad; };
+struct TcUnitIssueTable { TcUnitIssue u[kTcUnits]; };
+constexpr TcUnitIssueTable tc_make_unit_issue() {
+    TcUnitIssueTable t{};
+    for (int u = 0; u < kTcUnits; ++u) {
+        const int m = tc_unit_matrix(u);
+        t.u[u].a_hi = tc_hi_col(u); t.u[u].a_lo = tc_lo_col(u); t.u[u].a_left = tc_left_start(u);
+        t.u[u].b_hi = tc_matrix_offset(m, 0) >> 4; t.u[u].b_lo = tc_matrix_offset(m, 1) >> 4;
+        t.u[u].b_left0 = tc_left_offset(m, 0) >> 4; t.u[u].b_left1 = tc_left_offset(m, 1) >> 4;
+        t.u[u].pad = 0;
     }
-    // slots 96..101: one K step over the unit's [hi | lo] leftover columns, (hi + lo) Bh then hi Bl
-    const uint32_t a_left = tmem + tc_left_start(U);
-    mma_f16_ts<true>(d_tmem, a_left, desc0 + (tc_left_offset(m, 0) >> 4));
-    mma_f16_ts<true>(d_tmem, a_left, desc0 + (tc_left_offset(m, 1) >> 4));
+    return t;
 }
+__constant__ TcUnitIssue c_unit_issue[kTcUnits] = {tc_make_unit_issue().u[0], tc_make_unit_issue().u[1], tc_make_unit_issue().u[2],
+                                                   tc_make_unit_issue().u[3]};
 
 // ---- shared memory carve-up ----------------------------------------------------------------------
 constexpr int kSmemOperands = 0;                                                  // 139776 B, 128-byte aligned
@@ -434,6 +430,18 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
     const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol;
     uint32_t d_parity = 0, buf = 0;
     int ti = 0;
+    // Fused normalisation: this warp's share of an utterance is counted (the normaliser warps wait for the count) only
+    // after a fence that makes the tile's rows and extremes visible.  The fence waits for the warp's outstanding stores,
+    // so it is issued one tile late - just before the next tile's stores, when the previous ones have long drained.
+    int64_t pending_clip = -1;
+    auto count_tile = [&]() {
+        if (pending_clip >= 0) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) atomicAdd(a.done_counters + pending_clip, 1u);
+            pending_clip = -1;
+        }
+    };
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const TileCoord tc = tile_coord(tile, tiles_per_clip);
         // unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep)
@@ -444,6 +452,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
             if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
             d_parity ^= 1u;
         }
+        count_tile();
         // join the mels that straddle the split: half 1 hands its partial sums to half 0
         float* strad = s_straddle + ((buf * 4 + quad) * 3) * 32 + lane;
         if constexpr (HALF == 1) {
@@ -486,22 +495,23 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
             uint32_t inv = live ? ~max_key_encode(mn) : 0u;
             inv = __reduce_max_sync(0xffffffffu, inv);
             if (lane == 0) atomicMax(a.min_keys + tc.clip, inv);
-            // count this warp's share of the utterance: the normaliser warps of every CTA that holds one of its tiles
-            // wait for the count to be complete (8 epilogue warps per tile)
-            __threadfence();   // this tile's rows and max are visible before they are counted
-            __syncwarp();
-            if (lane == 0) atomicAdd(a.done_counters + tc.clip, 1u);
+            pending_clip = tc.clip;   // counted one tile later (count_tile), when its stores have long drained
         }
         if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
         if (HALF == 0 && trace != nullptr && blockIdx.x == 0 && quad == 0 && lane == 0 && ti < kTileStamps)
             trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + kTileStamps + ti] = clock64();
     }
+    count_tile();
 }
 
-template <typename InT, int NM>
+// BRINGUP = false is the production build: the timeline stamps and the staged bring-up modes (B200MEL_TC_TRACE,
+// B200MEL_TC_DEBUG) fold away, which also keeps the hot code inside the 32 KB instruction cache.
+template <typename InT, int NM, bool BRINGUP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ CUtensorMap audio_map, const int tma_rows,
-                 const unsigned char* __restrict__ operands, const int debug_stage, long long* __restrict__ trace, const int trace_first) {
+                 const unsigned char* __restrict__ operands, const int debug_arg, long long* __restrict__ trace_arg, const int trace_first) {
+    long long* const trace = BRINGUP ? trace_arg : nullptr;
+    const int debug_stage = BRINGUP ? debug_arg : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_audio = reinterpret_cast<float*>(smem_raw + kSmemAudio);
     float* s_straddle = reinterpret_cast<float*>(smem_raw + kSmemStraddle);
@@ -606,31 +616,42 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == kWarpMma && (debug_stage == 0 || debug_stage >= 3)) {
             // ===== tensor-core issue: the whole warp walks the loop, one elected lane issues =====
-            uint32_t desc0 = operand_desc_lo(smem_u32(smem_raw + kSmemOperands)), tmem_mma = tmem;
+            // One compact loop over the units (per-unit columns and matrix offsets from a constant table): the issue
+            // code stays small so it does not evict the fold and epilogue code from the instruction caches.
+            const uint32_t desc0 = operand_desc_lo(smem_u32(smem_raw + kSmemOperands)), d_tmem = tmem + kTcDCol;
+            const uint32_t a_full0 = smem_u32(&bars.a_full[0]), a_empty0 = smem_u32(&bars.a_empty[0]);
+            constexpr uint32_t kStep = (2 * kTcStripBytes) >> 4;   // K step s = strips 2s, 2s+1 = slots 16s..16s+15
             uint32_t a_parity = 0, d_parity = 1;   // d_empty: the first wait passes (accumulator starts free)
             int ti = 0;
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-                // u is a compile-time constant on purpose: with a run-time u, nvcc 12.9 folded &bars.a_empty[u >> 1]
-                // into base + 4 u (right only for even u) and the commit hit a misaligned mbarrier
-#pragma unroll
+#pragma unroll 1
                 for (int u = 0; u < kTcUnits; ++u) {
-                    if ((u & 1) == 0) { mbar_wait(&bars.a_full[u >> 1], a_parity); }
+                    const uint32_t sweep_bar = static_cast<uint32_t>(u & 2) << 2;   // byte offset of the sweep's barrier (0 or 8)
+                    if ((u & 1) == 0) mbar_wait_addr(a_full0 + sweep_bar, a_parity);
                     TC_TRACE(3, ti, 3 * u);
                     if (debug_stage != 3) mbar_wait(&bars.d_empty, d_parity);
                     else if (u > 0) { mbar_wait(&bars.d_full, (u - 1) & 1); }
                     d_parity ^= 1u;
                     TC_TRACE(3, ti, 3 * u + 1);
                     tc_fence_after();
-                    // keep the 80 descriptor / address constants out of registers: without this the compiler hoists every
-                    // base + constant out of the tile loop and spills them
-                    asm volatile("" : "+r"(desc0), "+r"(tmem_mma));
-                    if (u == 0) mma_issue_unit<0>(tmem_mma, desc0);
-                    else if (u == 1) mma_issue_unit<1>(tmem_mma, desc0);
-                    else if (u == 2) mma_issue_unit<2>(tmem_mma, desc0);
-                    else mma_issue_unit<3>(tmem_mma, desc0);
+                    const TcUnitIssue ui = c_unit_issue[u];
+                    uint32_t a_hi = tmem + ui.a_hi, a_lo = tmem + ui.a_lo, b_hi = desc0 + ui.b_hi, b_lo = desc0 + ui.b_lo;
+                    mma_f16_ts<false>(d_tmem, a_hi, b_hi);
+                    mma_f16_ts<true>(d_tmem, a_lo, b_hi);
+                    mma_f16_ts<true>(d_tmem, a_hi, b_lo);
+#pragma unroll 1
+                    for (int s = 1; s < kTcMainSteps; ++s) {
+                        a_hi += 8; a_lo += 8; b_hi += kStep; b_lo += kStep;
+                        mma_f16_ts<true>(d_tmem, a_hi, b_hi);
+                        mma_f16_ts<true>(d_tmem, a_lo, b_hi);
+                        mma_f16_ts<true>(d_tmem, a_hi, b_lo);
+                    }
+                    // slots 96..101: one K step over the unit's [hi | lo] leftover columns, (hi + lo) Bh then hi Bl
+                    mma_f16_ts<true>(d_tmem, tmem + ui.a_left, desc0 + ui.b_left0);
+                    mma_f16_ts<true>(d_tmem, tmem + ui.a_left, desc0 + ui.b_left1);
                     mma_commit(&bars.d_full);
                     TC_TRACE(3, ti, 3 * u + 2);
-                    if (u & 1) mma_commit(&bars.a_empty[u >> 1]);   // both units of the sweep have consumed its operand
+                    if (u & 1) mma_commit_addr(a_empty0 + sweep_bar);   // both units of the sweep have consumed its operand
                 }
                 a_parity ^= 1u;
             }
@@ -729,7 +750,9 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     if (err != cudaSuccess) return err;
     if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
     if (sms_by_device[device] == 0) {
-        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (err != cudaSuccess) return err;
         int sms = 0;
         if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return err;
@@ -792,8 +815,11 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     constexpr size_t kTraceBytes = sizeof(long long) * (kTraceWords + 6 * kStampCtas + TC_TILE_STAMPS);
     if (want_trace && trace == nullptr) { cudaMalloc(&trace, kTraceBytes); }
     if (want_trace) cudaMemsetAsync(trace, 0, kTraceBytes, stream);
-    logmel_tc_kernel<InT, NM><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, debug_stage,
-                                                                          want_trace ? trace : nullptr, trace_first);
+    if (want_trace || debug_stage != 0)
+        logmel_tc_kernel<InT, NM, true><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, debug_stage,
+                                                                                    want_trace ? trace : nullptr, trace_first);
+    else
+        logmel_tc_kernel<InT, NM, false><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, 0, nullptr, 0);
     count_launch();
     err = cudaGetLastError();
     if (want_trace && err == cudaSuccess) {   // bring-up only: synchronises and prints CTA 0's timeline
