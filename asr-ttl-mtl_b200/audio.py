@@ -16,6 +16,7 @@ optional ``lengths``, float32 or int16 PCM).
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 from functools import lru_cache
 from subprocess import CalledProcessError, run
@@ -147,6 +148,10 @@ def _validate_waveform(audio: torch.Tensor, allow_pcm16: bool) -> int:
     )
 
 
+# what "auto" means in this process: the library's own choice unless B200MEL_VARIANT names a kernel (tests flip it)
+DEFAULT_VARIANT = os.environ.get("B200MEL_VARIANT", "auto")
+
+
 def _frames_or_raise(n_samples: int, padding: int) -> int:
     try:
         return _native.frames(n_samples, padding)
@@ -177,6 +182,8 @@ def _run(audio: torch.Tensor, n_mels: int, padding: int, lengths, flags: int, va
     n_frames = _frames_or_raise(n_samples, padding)
     stride_b = wave.stride(0) if batch > 1 else n_samples
     shape = (batch, n_mels, n_frames)
+    if variant == "auto":
+        variant = DEFAULT_VARIANT
     try:
         variant_id = VARIANTS[variant]
     except KeyError:

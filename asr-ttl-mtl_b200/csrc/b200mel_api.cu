@@ -234,7 +234,9 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     if (plan == nullptr || out == nullptr || workspace == nullptr) return B200MEL_ERR_NULL_POINTER;
     if (dtype != B200MEL_F32 && dtype != B200MEL_S16) return B200MEL_ERR_BAD_ARGUMENT;
     if (batch < 0 || n_samples < 0 || stride_b < 0 || l2_chunk_clips < 0) return B200MEL_ERR_BAD_ARGUMENT;
-    if (variant == B200MEL_VARIANT_AUTO) variant = B200MEL_VARIANT_FFT;  // the variant ncu picked, see DESIGN.md
+    // the variant ncu picked: the tcgen05 kernel, unless this plan's filterbank could not be turned into its
+    // compile-time band tables - then the shared-memory FFT kernel, which takes any banded filterbank
+    if (variant == B200MEL_VARIANT_AUTO) variant = plan->d_tc_tables != nullptr ? B200MEL_VARIANT_TCGEN05 : B200MEL_VARIANT_FFT;
     if (variant != B200MEL_VARIANT_FFT && variant != B200MEL_VARIANT_TCGEN05) return B200MEL_ERR_BAD_ARGUMENT;
     if (variant == B200MEL_VARIANT_TCGEN05 && plan->d_tc_tables == nullptr) return B200MEL_ERR_BAD_FILTERS;
     int64_t n_frames = 0;

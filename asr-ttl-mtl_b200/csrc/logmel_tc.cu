@@ -396,112 +396,139 @@ __device__ __forceinline__ void sweep_store(int sweep, const float* fr, uint32_t
 static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) == 96 && tc_hi_col(3) - tc_hi_col(2) == 96 &&
               tc_left_col(1) - tc_left_col(0) == 6 && tc_left_col(3) - tc_left_col(2) == 6, "column arithmetic of sweep_store");
 
-// ---- epilogue helpers -----------------------------------------------------------------------------
-template <int NM, int HALF>
-__device__ __forceinline__ void epilogue_unit(int unit, uint32_t d_addr, uint64_t* d_full, uint64_t* d_empty, uint32_t parity,
-                                              int lane, float (&acc)[TcEpilogueLayout<NM>::acc_size(HALF)], long long* trace, const int trace_first, int ti, int quad) {
-    using L = TcEpilogueLayout<NM>;
-    float d[L::cols(HALF)];
-    mbar_wait(d_full, parity);
-    tc_fence_after();
-    tmem_ld_cols<L::cols(HALF)>(d_addr + L::col0(HALF), d);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(d_empty);   // the accumulator is in registers: the next unit may overwrite it
-    if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * (unit < 0 ? 0 : unit) + 1);
-    switch (unit) {
-        case -1: acc[0] += d[0] + d[L::cols(HALF) - 1]; break;   // bring-up: loads only
-        // Re and Im of a bin take the same weights: units 0 / 2 (even bins) share one body, units 1 / 3 (odd bins) the other
-        case 0: case 2: tc_epilogue_unit<NM, 0, HALF>(d, acc); break;
-        default: tc_epilogue_unit<NM, 1, HALF>(d, acc); break;
-    }
-}
+// ---- epilogue ---------------------------------------------------------------------------------------
+// Hand-shake between the epilogue warps and the normaliser warps for the rare tiles that need the clamp: the rows an
+// epilogue warp stored become visible to the normaliser only after a gpu-scope fence, which costs ~1000 cycles - so
+// the epilogue fences only once a normaliser warp has asked for it (slow_mode), and publishes how far it has fenced.
+struct TcNormState {
+    uint32_t slow_mode;          // set by a normaliser warp that found a tile to clamp; never cleared
+    uint32_t fenced_below[8];    // per epilogue warp: its rows of tiles with ordinal < this are visible gpu-wide
+};
 
 template <int NM, int HALF>
 __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, long long* trace, const int trace_first, TcBarriers* bars,
-                                              float* s_straddle,
+                                              TcNormState* norm, float* s_straddle,
                                               uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
     using L = TcEpilogueLayout<NM>;
     constexpr int ACC = L::acc_size(HALF);
     float acc[ACC];
 #pragma unroll
     for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
-    const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol;
+    const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol + L::col0(HALF);
+    const int me = 4 * HALF + quad;                                  // index among the 8 epilogue warps
+    volatile uint32_t* const slow_mode = &norm->slow_mode;
     uint32_t d_parity = 0, buf = 0;
-    int ti = 0;
-    // Fused normalisation: this warp's share of an utterance is counted (the normaliser warps wait for the count) only
-    // after a fence that makes the tile's rows and extremes visible.  The fence waits for the warp's outstanding stores,
-    // so it is issued one tile late - just before the next tile's stores, when the previous ones have long drained.
+    // Fused normalisation: this warp's share of an utterance is counted (the normaliser warps wait for the count) one
+    // tile late.  The count must follow the utterance's extremes: the two atomics return their old values, and the
+    // count is issued only once those have come back (a register dependency instead of a fence).
     int64_t pending_clip = -1;
-    auto count_tile = [&]() {
-        if (pending_clip >= 0) {
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) atomicAdd(a.done_counters + pending_clip, 1u);
-            pending_clip = -1;
-        }
-    };
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const TileCoord tc = tile_coord(tile, tiles_per_clip);
-        // unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep)
+    uint32_t old_max = 0, old_min = 0;
+    const int64_t my_tiles = static_cast<int64_t>(blockIdx.x) < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    TileCoord prev{0, 0};
+    // One pass per tile plus a last pass that only finishes the final tile.  A tile is FINISHED (log10, stores,
+    // extremes) after unit 0 of the next tile has been pulled out of the accumulator, so the tensor cores run the next
+    // unit while the stores go out; unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep).
+#pragma unroll 1
+    for (int64_t k = 0; k <= my_tiles; ++k) {
+        const bool more = k < my_tiles;
+        const int ti = static_cast<int>(k);
 #pragma unroll 1
         for (int u = 0; u < kTcUnits; ++u) {
-            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u);
-            epilogue_unit<NM, HALF>(debug_stage == 4 ? -1 : u, d_addr, &bars->d_full, &bars->d_empty, d_parity, lane, acc, trace, trace_first, ti, quad);
-            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
-            d_parity ^= 1u;
-        }
-        count_tile();
-        // join the mels that straddle the split: half 1 hands its partial sums to half 0
-        float* strad = s_straddle + ((buf * 4 + quad) * 3) * 32 + lane;
-        if constexpr (HALF == 1) {
-#pragma unroll
-            for (int j = 0; j < L::straddle; ++j) strad[j * 32] = acc[j];
-        }
-        if constexpr (L::straddle > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-        if constexpr (HALF == 0) {
-#pragma unroll
-            for (int j = 0; j < L::straddle; ++j) acc[L::high_base + j] += strad[j * 32];
-        }
-        buf ^= 1u;
-        // log10 clamp, coalesced row stores (lane = frame), utterance max
-        const int f = quad * 32 + lane, t = tc.t0 + f;
-        const bool live = t < a.n_frames;
-        constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
-        const int64_t pitch = a.n_frames;
-        float* out = a.out + (tc.clip * NM + m_begin) * pitch + t;
-        // With the normalisation fused, the affine half of it, (x + 4) / 4, is applied here (one FFMA, the same single
-        // rounding as audio.py:156) and only the clamp at max - 8 is left for the normaliser warps - which skip the
-        // utterance when its smallest value is not below max - 8 (tracked here as well).
-        float mx = __uint_as_float(0xff800000u), mn = __uint_as_float(0x7f800000u);
-        if (live) {
-            const float scale = a.fused_norm ? 0.25f : 1.0f, shift = a.fused_norm ? 1.0f : 0.0f;
-#pragma unroll
-            for (int m = m_begin; m < m_end; ++m) {
-                const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
-                *out = fmaf(lg, scale, shift);
-                out += pitch;
-                mx = max_nan(mx, lg);
-                mn = fminf(mn, lg);
+            float d[L::cols(HALF)];
+            if (more) {
+                if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u);
+                mbar_wait(&bars->d_full, d_parity);
+                d_parity ^= 1u;
+                tc_fence_after();
+                tmem_ld_cols<L::cols(HALF)>(d_addr, d);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->d_empty);   // the accumulator is in registers: the next unit may overwrite it
+                if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 1);
             }
-        }
+            if (u == 0 && k > 0) {
+                // ---- finish the previous tile ----
+                if (pending_clip >= 0) {                       // count the tile before it
+                    const bool fence = *slow_mode != 0;
+                    if (fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                    asm volatile("" ::"r"(old_max), "r"(old_min) : "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        atomicAdd(a.done_counters + pending_clip, 1u);
+                        if (fence) *reinterpret_cast<volatile uint32_t*>(&norm->fenced_below[me]) = static_cast<uint32_t>(k - 1);
+                    }
+                    pending_clip = -1;
+                }
+                // join the mels that straddle the split: half 1 hands its partial sums to half 0
+                float* strad = s_straddle + ((buf * 4 + quad) * 3) * 32 + lane;
+                if constexpr (HALF == 1) {
 #pragma unroll
-        for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
-        uint32_t key = live ? max_key_encode(mx) : 0u;
-        key = __reduce_max_sync(0xffffffffu, key);
-        if (lane == 0) atomicMax(a.max_keys + (a.global_max ? 0 : tc.clip), key);
-        if (a.fused_norm) {
-            uint32_t inv = live ? ~max_key_encode(mn) : 0u;
-            inv = __reduce_max_sync(0xffffffffu, inv);
-            if (lane == 0) atomicMax(a.min_keys + tc.clip, inv);
-            pending_clip = tc.clip;   // counted one tile later (count_tile), when its stores have long drained
+                    for (int j = 0; j < L::straddle; ++j) strad[j * 32] = acc[j];
+                }
+                if constexpr (L::straddle > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                if constexpr (HALF == 0) {
+#pragma unroll
+                    for (int j = 0; j < L::straddle; ++j) acc[L::high_base + j] += strad[j * 32];
+                }
+                buf ^= 1u;
+                // log10 clamp, coalesced row stores (lane = frame), utterance extremes
+                const int f = quad * 32 + lane, t = prev.t0 + f;
+                const bool live = t < a.n_frames;
+                constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
+                const int64_t pitch = a.n_frames;
+                float* out = a.out + (prev.clip * NM + m_begin) * pitch + t;
+                // With the normalisation fused, the affine half of it, (x + 4) / 4, is applied here (one FFMA, the same
+                // single rounding as audio.py:156) and only the clamp at max - 8 is left for the normaliser warps - which
+                // skip the utterance when its smallest value is not below max - 8 (tracked here as well).
+                float mx = __uint_as_float(0xff800000u), mn = __uint_as_float(0x7f800000u);
+                if (live) {
+                    const float scale = a.fused_norm ? 0.25f : 1.0f, shift = a.fused_norm ? 1.0f : 0.0f;
+#pragma unroll
+                    for (int m = m_begin; m < m_end; ++m) {
+                        const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
+                        *out = fmaf(lg, scale, shift);
+                        out += pitch;
+                        mx = max_nan(mx, lg);
+                        mn = fminf(mn, lg);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
+                uint32_t key = live ? max_key_encode(mx) : 0u;
+                key = __reduce_max_sync(0xffffffffu, key);
+                if (a.fused_norm) {
+                    uint32_t inv = live ? ~max_key_encode(mn) : 0u;
+                    inv = __reduce_max_sync(0xffffffffu, inv);
+                    if (lane == 0) {
+                        old_max = atomicMax(a.max_keys + (a.global_max ? 0 : prev.clip), key);
+                        old_min = atomicMax(a.min_keys + prev.clip, inv);
+                    }
+                    pending_clip = prev.clip;   // counted at the next finish
+                } else if (lane == 0) {
+                    atomicMax(a.max_keys + (a.global_max ? 0 : prev.clip), key);
+                }
+                if (quad == 0) TC_TRACE(4 + HALF, ti - 1, 12);
+                if (HALF == 0 && trace != nullptr && blockIdx.x == 0 && quad == 0 && lane == 0 && ti - 1 < kTileStamps)
+                    trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + kTileStamps + ti - 1] = clock64();
+            }
+            if (!more) break;
+            // Re and Im of a bin take the same weights: units 0 / 2 (even bins) share one body, units 1 / 3 (odd bins) the other
+            if (debug_stage == 4) acc[0] += d[0] + d[L::cols(HALF) - 1];   // bring-up: loads only
+            else if ((u & 1) == 0) tc_epilogue_unit<NM, 0, HALF>(d, acc);
+            else tc_epilogue_unit<NM, 1, HALF>(d, acc);
+            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
         }
-        if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
-        if (HALF == 0 && trace != nullptr && blockIdx.x == 0 && quad == 0 && lane == 0 && ti < kTileStamps)
-            trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + kTileStamps + ti] = clock64();
+        if (more) prev = tile_coord(blockIdx.x + k * gridDim.x, tiles_per_clip);
     }
-    count_tile();
+    // the last tile is counted behind an unconditional fence; after it every row of this warp is visible
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("" ::"r"(old_max), "r"(old_min) : "memory");
+    __syncwarp();
+    if (lane == 0) {
+        if (pending_clip >= 0) atomicAdd(a.done_counters + pending_clip, 1u);
+        *reinterpret_cast<volatile uint32_t*>(&norm->fenced_below[me]) = 0xffffffffu;
+    }
 }
 
 // BRINGUP = false is the production build: the timeline stamps and the staged bring-up modes (B200MEL_TC_TRACE,
@@ -516,6 +543,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     float* s_audio = reinterpret_cast<float*>(smem_raw + kSmemAudio);
     float* s_straddle = reinterpret_cast<float*>(smem_raw + kSmemStraddle);
     __shared__ __align__(8) TcBarriers bars;
+    __shared__ TcNormState norm_state;
     __shared__ uint32_t s_tmem;
 
     // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from
@@ -549,6 +577,8 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
         mbar_init(&bars.d_full, 1);
         mbar_init(&bars.d_empty, 8);
+        norm_state.slow_mode = 0;
+        for (int i = 0; i < 8; ++i) norm_state.fenced_below[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -610,8 +640,8 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         // ===== epilogue warps =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         if (debug_stage > 0 && debug_stage < 4) total_tiles = 0;
-        if (warp < kWarpEpi1) epilogue_role<NM, 0>(a, debug_stage, trace, trace_first, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
-        else epilogue_role<NM, 1>(a, debug_stage, trace, trace_first, &bars, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        if (warp < kWarpEpi1) epilogue_role<NM, 0>(a, debug_stage, trace, trace_first, &bars, &norm_state, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        else epilogue_role<NM, 1>(a, debug_stage, trace, trace_first, &bars, &norm_state, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == kWarpMma && (debug_stage == 0 || debug_stage >= 3)) {
@@ -711,9 +741,25 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                     fix = !(smallest >= g - 8.0f);    // nothing below the clamp: leave the utterance alone (false for a NaN max)
                 }
                 unsigned todo = __ballot_sync(0xffffffffu, fix);
+                if (todo != 0) {
+                    // ask the epilogue warps to fence what they store from now on (see TcNormState) ...
+                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&norm_state.slow_mode) = 1u;
+                    __syncwarp();
+                }
                 while (todo != 0) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
+                    // ... and wait until every one of them has fenced the rows of this tile (ordinal g0 + src)
+                    if (lane < 8) {
+                        const volatile uint32_t* fenced = &norm_state.fenced_below[lane];
+                        uint32_t polls = 0;
+                        while (*fenced <= static_cast<uint32_t>(g0 + src)) {
+                            if (++polls > (1u << 21)) tc_fault(0x3000000u | (static_cast<uint32_t>(g0 + src) << 8 & 0xffff00u) | (threadIdx.x >> 5));
+                            __nanosleep(500);
+                        }
+                    }
+                    __syncwarp();
+                    __threadfence();
                     const int64_t clip = __shfl_sync(0xffffffffu, static_cast<int>(tc.clip), src);
                     const int t0 = __shfl_sync(0xffffffffu, tc.t0, src);
                     const float gs = __shfl_sync(0xffffffffu, g, src);

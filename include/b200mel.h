@@ -52,7 +52,7 @@ typedef enum b200mel_dtype {
 } b200mel_dtype;
 
 typedef enum b200mel_variant {
-    B200MEL_VARIANT_AUTO = 0,   /* the variant ncu picked                 */
+    B200MEL_VARIANT_AUTO = 0,   /* the variant ncu picked: tcgen05        */
     B200MEL_VARIANT_FFT = 1,    /* shared-memory mixed-radix (20x20) real FFT, fp32 CUDA cores */
     B200MEL_VARIANT_TCGEN05 = 2 /* DFT-as-GEMM on tcgen05 tensor cores, 3xTF32 compensation    */
 } b200mel_variant;

@@ -16,6 +16,17 @@ DEV = "cuda:0"
 VARIANTS = ["fft", "tcgen05"]
 
 
+@pytest.fixture(autouse=True, params=VARIANTS)
+def default_variant(request, b200):
+    """Every test below runs once per STFT kernel: "auto" (what the unchanged consumers get) is pinned to each in turn."""
+    from asr_ttl_mtl_b200 import audio as audio_module
+
+    saved = audio_module.DEFAULT_VARIANT
+    audio_module.DEFAULT_VARIANT = request.param
+    yield request.param
+    audio_module.DEFAULT_VARIANT = saved
+
+
 def _maxerr(a, b):
     return float((torch.as_tensor(a).double().cpu() - torch.as_tensor(b).double().cpu()).abs().max())
 
