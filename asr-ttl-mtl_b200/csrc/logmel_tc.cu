@@ -460,6 +460,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                     }
                     pending_clip = -1;
                 }
+                if (quad == 0) TC_TRACE(4 + HALF, ti - 1, 13);
                 // join the mels that straddle the split: half 1 hands its partial sums to half 0
                 float* strad = s_straddle + ((buf * 4 + quad) * 3) * 32 + lane;
                 if constexpr (HALF == 1) {
@@ -472,29 +473,31 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                     for (int j = 0; j < L::straddle; ++j) acc[L::high_base + j] += strad[j * 32];
                 }
                 buf ^= 1u;
+                if (quad == 0) TC_TRACE(4 + HALF, ti - 1, 14);
                 // log10 clamp, coalesced row stores (lane = frame), utterance extremes
                 const int f = quad * 32 + lane, t = prev.t0 + f;
                 const bool live = t < a.n_frames;
                 constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
                 const int64_t pitch = a.n_frames;
-                float* out = a.out + (prev.clip * NM + m_begin) * pitch + t;
+                float* const out = a.out + (prev.clip * NM + m_begin) * pitch + t;
                 // With the normalisation fused, the affine half of it, (x + 4) / 4, is applied here (one FFMA, the same
                 // single rounding as audio.py:156) and only the clamp at max - 8 is left for the normaliser warps - which
                 // skip the utterance when its smallest value is not below max - 8 (tracked here as well).
                 float mx = __uint_as_float(0xff800000u), mn = __uint_as_float(0x7f800000u);
                 if (live) {
                     const float scale = a.fused_norm ? 0.25f : 1.0f, shift = a.fused_norm ? 1.0f : 0.0f;
+                    const uint32_t pitch32 = static_cast<uint32_t>(a.n_frames);
 #pragma unroll
                     for (int m = m_begin; m < m_end; ++m) {
                         const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
-                        *out = fmaf(lg, scale, shift);
-                        out += pitch;
+                        out[static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin)] = fmaf(lg, scale, shift);
                         mx = max_nan(mx, lg);
                         mn = fminf(mn, lg);
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
+                if (quad == 0) TC_TRACE(4 + HALF, ti - 1, 15);
                 uint32_t key = live ? max_key_encode(mx) : 0u;
                 key = __reduce_max_sync(0xffffffffu, key);
                 if (a.fused_norm) {
