@@ -343,7 +343,23 @@ def run_own_arm(args) -> None:
         "clips_per_step_per_gpu": e2e_batch,
         "steps": e2e_steps,
         "api": "log_mel_spectrogram_batch(pinned CPU tensor) -> b200mel_logmel_host",
+        "bound": "PCIe 5.0 x16: 491.5 MB in + 245.8 MB out per step, both directions at once take 9.5 ms on this pool "
+                 "(tools/pcie_bw.py) = 225 audio-hours/s",
     }
+    # The same call fed with int16 PCM (what load_audio decodes before it scales by 1/32768, audio.py:62):
+    # half the host-to-device bytes, bit-equal output.  Reported beside the fp32 number, not instead of it.
+    host_pcm = (host_in * 32768.0).round().clamp_(-32768, 32767).to(torch.int16).pin_memory()
+    for _ in range(2):
+        b200.log_mel_spectrogram_batch(host_pcm, n_mels=n_mels, out=host_out, variant=args.variant)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        b200.log_mel_spectrogram_batch(host_pcm, n_mels=n_mels, out=host_out, variant=args.variant)
+    torch.cuda.synchronize()
+    pcm_s = max_over_ranks(time.perf_counter() - t0)
+    e2e["pcm16_input"] = {"value": e2e_clips * CLIP_SECONDS / 3600.0 / pcm_s, "unit": "audio-hours/s",
+                          "h2d_bytes_per_step": e2e_batch * N_SAMPLES * 2}
 
     if rank == 0:
         cpu = cpu_baseline(n_mels, args.cpu_seconds) if world == 1 and not args.no_cpu_baseline else None
