@@ -20,6 +20,7 @@ ERR_NULL_POINTER, ERR_BAD_N_MELS, ERR_TOO_SHORT, ERR_BAD_ARGUMENT, ERR_BAD_FILTE
 DTYPE_F32, DTYPE_S16 = 0, 1
 VARIANT_AUTO, VARIANT_FFT, VARIANT_TCGEN05 = 0, 1, 2
 FLAG_GLOBAL_MAX = 1
+FLAG_TILE_KEYS = 2
 ABI_VERSION = 1
 
 #: every symbol include/b200mel.h declares: (restype, argtypes)
@@ -32,6 +33,7 @@ SYMBOLS = {
     "b200mel_plan_destroy": (c_int, [c_void_p]),
     "b200mel_plan_n_mels": (c_int, [c_void_p]),
     "b200mel_workspace_bytes": (c_size_t, [c_int64]),
+    "b200mel_workspace_bytes_tiles": (c_size_t, [c_int64, c_int64]),
     "b200mel_logmel_device": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                       c_void_p, c_void_p, c_uint, c_int, c_int, c_void_p]),
     "b200mel_normalise_device": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_uint, c_void_p]),

@@ -203,11 +203,11 @@ def _run(audio: torch.Tensor, n_mels: int, padding: int, lengths, flags: int, va
                 if lengths.shape != (batch,):
                     raise ValueError(f"lengths must have shape ({batch},)")
                 len_ptr = lengths.data_ptr()
-            workspace = torch.empty(lib.b200mel_workspace_bytes(batch), dtype=torch.uint8, device=wave.device)
+            workspace = torch.empty(lib.b200mel_workspace_bytes_tiles(batch, n_frames), dtype=torch.uint8, device=wave.device)
             stream = torch.cuda.current_stream(wave.device)
             _native.check(lib.b200mel_logmel_device(
                 plan, wave.data_ptr(), dtype, batch, n_samples, stride_b, len_ptr, padding, out.data_ptr(),
-                workspace.data_ptr(), flags, variant_id, int(l2_chunk_clips), stream.cuda_stream))
+                workspace.data_ptr(), flags | _native.FLAG_TILE_KEYS, variant_id, int(l2_chunk_clips), stream.cuda_stream))
             # the caching allocator may hand these blocks to another stream once we return
             workspace.record_stream(stream)
             wave.record_stream(stream)

@@ -218,6 +218,15 @@ size_t b200mel_workspace_bytes(int64_t batch) {
     return round_up(workspace_words(batch) * sizeof(uint32_t), 256);
 }
 
+// ... followed, with B200MEL_FLAG_TILE_KEYS, by [tile keys: batch * ceil(T / 128) * 2 u32] at the next 256-byte boundary
+static_assert(kTcTileFrames == 128, "tile-key layout");
+static int64_t tc_tiles_per_clip(int64_t n_frames) { return (n_frames + kTcTileFrames - 1) / kTcTileFrames; }
+size_t b200mel_workspace_bytes_tiles(int64_t batch, int64_t n_frames) {
+    if (batch < 1) batch = 1;
+    if (n_frames < 1) n_frames = 1;
+    return b200mel_workspace_bytes(batch) + round_up(static_cast<size_t>(batch) * tc_tiles_per_clip(n_frames) * 2 * sizeof(uint32_t), 256);
+}
+
 int b200mel_normalise_device(float* out, const void* workspace, int64_t batch, int64_t elems_per_clip,
                              unsigned flags, void* stream) {
     if (out == nullptr || workspace == nullptr) return B200MEL_ERR_NULL_POINTER;
@@ -270,6 +279,11 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     a.done_counters = keys + batch;
     a.tile_counter = keys + 2 * batch;
     a.min_keys = keys + 2 * batch + 1;
+    a.tile_keys = nullptr;
+    if ((flags & B200MEL_FLAG_TILE_KEYS) && variant == B200MEL_VARIANT_TCGEN05) {
+        a.tile_keys = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + b200mel_workspace_bytes(batch));
+        B200_CUDA(cudaMemsetAsync(a.tile_keys, 0, static_cast<size_t>(batch) * tc_tiles_per_clip(n_frames) * 2 * sizeof(uint32_t), stream));
+    }
     a.global_max = global_max;
     // one max per utterance (or a single utterance, where the call's max is the utterance's): normalised inside the
     // front-end kernel.  The FFT variant's last CTA normalises the whole utterance, so very long ones go to pass 2;
@@ -324,7 +338,7 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
         B200_CUDA(cudaStreamSynchronize(s.stream));
         B200_CUDA(ensure(&s.d_in, &s.in_bytes, static_cast<size_t>(n) * n_samples * in_elem + 16));
         B200_CUDA(ensure(reinterpret_cast<void**>(&s.d_out), &s.out_bytes, static_cast<size_t>(n) * elems_per_clip * 4));
-        B200_CUDA(ensure(&s.d_ws, &s.ws_bytes, b200mel_workspace_bytes(n)));
+        B200_CUDA(ensure(&s.d_ws, &s.ws_bytes, b200mel_workspace_bytes_tiles(n, n_frames)));
         const char* src = static_cast<const char*>(audio_host) + static_cast<size_t>(c0) * stride_b * in_elem;
         if (stride_b == n_samples || n == 1) {
             B200_CUDA(cudaMemcpyAsync(s.d_in, src, static_cast<size_t>(n) * n_samples * in_elem, cudaMemcpyHostToDevice, s.stream));
@@ -340,7 +354,7 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
             d_len = s.d_len;
         }
         result = b200mel_logmel_device(plan, s.d_in, dtype, n, n_samples, n_samples, d_len, right_zero_pad, s.d_out,
-                                       s.d_ws, flags, variant, 0, s.stream);
+                                       s.d_ws, flags | B200MEL_FLAG_TILE_KEYS, variant, 0, s.stream);
         if (result != B200MEL_OK) break;
         B200_CUDA(cudaMemcpyAsync(out_host + c0 * elems_per_clip, s.d_out, static_cast<size_t>(n) * elems_per_clip * 4,
                                   cudaMemcpyDeviceToHost, s.stream));

@@ -25,6 +25,7 @@ struct LogmelArgs {
     uint32_t* tile_counter;  // device, [1]: the persistent kernel's tile queue head
     uint32_t* min_keys;      // device, [batch]: ~key of the utterance's smallest log10 value (tcgen05 variant: decides
                              // whether the dynamic-range clamp touches the utterance at all)
+    uint32_t* tile_keys;     // device, [tiles of 128 frames][2] or nullptr: max key and ~min key of every tile (tcgen05)
     int global_max;
     int fused_norm;          // the last CTA to finish an utterance normalises it in place
     int n_rows;              // rows of the mel partial-sum tile (DeviceTables::n_rows)

@@ -224,6 +224,21 @@ __device__ __forceinline__ float4 normalise4(float4 x, float f) {
     return x;
 }
 
+// one warp overwrites one tile with the clamp value (every value of the tile was below it): stores only
+template <int NM>
+__device__ __forceinline__ void fill_tile_tc(float* __restrict__ tile_out, int64_t pitch, int frames, float v, int lane) {
+    if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & 15u) == 0 && (frames & 3) == 0) {
+        if (lane < (frames >> 2)) {
+            float* p = tile_out + 4 * lane;
+            const float4 v4 = make_float4(v, v, v, v);
+#pragma unroll 4
+            for (int row = 0; row < NM; ++row, p += pitch) *reinterpret_cast<float4*>(p) = v4;
+        }
+    } else {
+        for (int i = lane; i < NM * frames; i += 32) tile_out[(i / frames) * pitch + i % frames] = v;
+    }
+}
+
 // one warp clamps one tile (NM rows of `frames` values at `pitch`) in place
 template <int NM>
 __device__ __forceinline__ void normalise_tile_tc(float* __restrict__ tile_out, int64_t pitch, int frames, float g /* the clamp in rescaled units */, int lane) {
@@ -340,6 +355,14 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
     const int64_t valid = valid_samples(a, tc.clip);
     const int64_t s0 = static_cast<int64_t>(tc.t0) * kHop - kHalfWin;
     const bool aligned = sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
+    if (s0 >= valid && valid + kHalfWin < a.total) {
+        // the whole tile lies in the zero tail (`lengths`, right padding) and no reflection reaches a real sample
+        float4* z = reinterpret_cast<float4*>(s_audio);
+        for (int i = pt; i < kTcAudioWords / 4; i += kProducerThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        if ((pt & 31) == 0) mbar_arrive(full);
+        return;
+    }
     // chunk c = 40 r + k covers samples s0 + 4c .. + 3 and lands at word 164 r + 4 k
     int r = pt / kChunksPerRow, k = pt - r * kChunksPerRow;
     for (int c = pt; c < kTileChunks; c += kProducerThreads) {
@@ -422,7 +445,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
     // tile late.  The count must follow the utterance's extremes: the two atomics return their old values, and the
     // count is issued only once those have come back (a register dependency instead of a fence).
     int64_t pending_clip = -1;
-    uint32_t old_max = 0, old_min = 0;
+    uint32_t old_max = 0, old_min = 0, old_tile_max = 0, old_tile_min = 0;
     const int64_t my_tiles = static_cast<int64_t>(blockIdx.x) < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TileCoord prev{0, 0};
     // One pass per tile plus a last pass that only finishes the final tile.  A tile is FINISHED (log10, stores,
@@ -452,7 +475,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                 if (pending_clip >= 0) {                       // count the tile before it
                     const bool fence = *slow_mode != 0;
                     if (fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                    asm volatile("" ::"r"(old_max), "r"(old_min) : "memory");
+                    asm volatile("" ::"r"(old_max), "r"(old_min), "r"(old_tile_max), "r"(old_tile_min) : "memory");
                     __syncwarp();
                     if (lane == 0) {
                         atomicAdd(a.done_counters + pending_clip, 1u);
@@ -506,6 +529,11 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                     if (lane == 0) {
                         old_max = atomicMax(a.max_keys + (a.global_max ? 0 : prev.clip), key);
                         old_min = atomicMax(a.min_keys + prev.clip, inv);
+                        if (a.tile_keys != nullptr) {   // the tile's own extremes: lets the clamp path skip or fill whole tiles
+                            uint32_t* tk = a.tile_keys + 2 * (static_cast<int64_t>(blockIdx.x) + (k - 1) * gridDim.x);
+                            old_tile_max = atomicMax(tk, key);
+                            old_tile_min = atomicMax(tk + 1, inv);
+                        }
                     }
                     pending_clip = prev.clip;   // counted at the next finish
                 } else if (lane == 0) {
@@ -526,7 +554,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
     }
     // the last tile is counted behind an unconditional fence; after it every row of this warp is visible
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    asm volatile("" ::"r"(old_max), "r"(old_min) : "memory");
+    asm volatile("" ::"r"(old_max), "r"(old_min), "r"(old_tile_max), "r"(old_tile_min) : "memory");
     __syncwarp();
     if (lane == 0) {
         if (pending_clip >= 0) atomicAdd(a.done_counters + pending_clip, 1u);
@@ -737,13 +765,22 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 __syncwarp();
                 __threadfence();   // the extremes (and the rows) are read after the counts
                 float g = 0.f;
-                bool fix = false;
+                int action = 0;                        // 0: leave the tile alone, 1: clamp it in place, 2: fill it with the clamp value
                 if (have) {
                     g = max_key_decode(__ldcg(a.max_keys + tc.clip));
+                    const float floor_lg = g - 8.0f;
                     const float smallest = max_key_decode(~__ldcg(a.min_keys + tc.clip));
-                    fix = !(smallest >= g - 8.0f);    // nothing below the clamp: leave the utterance alone (false for a NaN max)
+                    if (!(smallest >= floor_lg)) {     // something in the utterance is below the clamp (or the max is NaN)
+                        action = 1;
+                        if (a.tile_keys != nullptr) {
+                            const uint32_t* tk = a.tile_keys + 2 * (static_cast<int64_t>(blockIdx.x) + (g0 + lane) * gridDim.x);
+                            const float tile_max = max_key_decode(__ldcg(tk)), tile_min = max_key_decode(~__ldcg(tk + 1));
+                            if (tile_min >= floor_lg) action = 0;          // this tile is wholly above the clamp
+                            else if (tile_max < floor_lg) action = 2;      // wholly below it (digital silence, zero padding)
+                        }
+                    }
                 }
-                unsigned todo = __ballot_sync(0xffffffffu, fix);
+                unsigned todo = __ballot_sync(0xffffffffu, action != 0);
                 if (todo != 0) {
                     // ask the epilogue warps to fence what they store from now on (see TcNormState) ...
                     if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&norm_state.slow_mode) = 1u;
@@ -766,9 +803,12 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                     const int64_t clip = __shfl_sync(0xffffffffu, static_cast<int>(tc.clip), src);
                     const int t0 = __shfl_sync(0xffffffffu, tc.t0, src);
                     const float gs = __shfl_sync(0xffffffffu, g, src);
+                    const bool fill = __shfl_sync(0xffffffffu, action, src) == 2;
                     const int frames = a.n_frames - t0 < kTcTileFrames ? a.n_frames - t0 : kTcTileFrames;
                     const float floor_y = ((gs - 8.0f) + 4.0f) * 0.25f;
-                    normalise_tile_tc<NM>(a.out + clip * NM * static_cast<int64_t>(a.n_frames) + t0, a.n_frames, frames, floor_y, lane);
+                    float* tile_out = a.out + clip * NM * static_cast<int64_t>(a.n_frames) + t0;
+                    if (fill) fill_tile_tc<NM>(tile_out, a.n_frames, frames, floor_y, lane);
+                    else normalise_tile_tc<NM>(tile_out, a.n_frames, frames, floor_y, lane);
                 }
             }
         }

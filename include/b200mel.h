@@ -62,6 +62,11 @@ typedef enum b200mel_variant {
                                       behaviour for a 2-D input (audio.py:155).  Default is one
                                       max per utterance (stack of per-clip calls).             */
 
+#define B200MEL_FLAG_TILE_KEYS 2u  /* `workspace` was sized with b200mel_workspace_bytes_tiles: the tcgen05 kernel
+                                      also keeps the extremes of every 128-frame tile there, so that the clamp at
+                                      max - 8 (audio.py:155) re-touches only the tiles it changes: silent (zero-padded)
+                                      tiles are filled, tiles wholly above the clamp are left alone.           */
+
 typedef struct b200mel_plan b200mel_plan; /* opaque: filterbank bands + FFT tables on one device */
 
 int b200mel_abi_version(void);
@@ -82,6 +87,9 @@ int b200mel_plan_n_mels(const b200mel_plan* plan);
 
 /* Bytes of device scratch b200mel_logmel_device needs for `batch` utterances. */
 size_t b200mel_workspace_bytes(int64_t batch);
+/* The same plus room for per-tile extremes (pass B200MEL_FLAG_TILE_KEYS with a workspace of this size);
+ * n_frames from b200mel_frames. */
+size_t b200mel_workspace_bytes_tiles(int64_t batch, int64_t n_frames);
 
 /* Replaces log_mel_spectrogram's compute, audio.py:145-156, for a batch of utterances.
  *   audio      device, [batch, n_samples] of `dtype`, row pitch `stride_b` ELEMENTS
@@ -89,7 +97,8 @@ size_t b200mel_workspace_bytes(int64_t batch);
  *              row is treated as zeros WITHOUT being read (pad_or_trim semantics, audio.py:83-86)
  *   right_zero_pad  the `padding` argument (audio.py:145-146); <= 0 is ignored
  *   out        device float32 [batch, n_mels, T] contiguous, T from b200mel_frames
- *   workspace  device scratch of b200mel_workspace_bytes(batch)
+ *   workspace  device scratch of b200mel_workspace_bytes(batch), or of b200mel_workspace_bytes_tiles(batch, T)
+ *              together with B200MEL_FLAG_TILE_KEYS
  *   l2_chunk_clips  reserved (0): the persistent kernel walks the batch utterance-major, so an
  *              utterance is normalised while its un-normalised values are still in L2
  */

@@ -140,6 +140,30 @@ def test_variable_length_clips_like_the_training_set(b200):
             assert abs(float(got[i].max() - tail.flatten()[0]) - 2.0) < 1e-6
 
 
+def test_dynamic_range_clamp_paths(b200):
+    """The clamp at max - 8 (audio.py:155) when it touches whole tiles (digital silence), parts of tiles (a noise floor
+    100 dB down, a loud click in a quiet clip) and nothing at all - the tcgen05 kernel treats each case differently."""
+    rng = np.random.default_rng(5)
+    n = 16000 * 12
+    loud = (0.2 * rng.standard_normal(n)).astype(np.float32)
+    clips = np.zeros((5, n), dtype=np.float32)
+    clips[0] = loud                                              # nothing below the clamp
+    clips[1, : n // 3] = loud[: n // 3]                          # speech, then digital silence (tiles to fill)
+    clips[2] = loud
+    clips[2, n // 4: n // 2] *= 1e-5                             # a stretch 100 dB down: clamped value by value
+    clips[3] = 1e-4 * loud
+    clips[3, 70000:70040] = 0.9                                  # one click sets the max; the rest is mostly below max - 8
+    clips[4, 1000] = 1.0                                         # an impulse in silence
+    got = b200.log_mel_spectrogram_batch(torch.from_numpy(clips).to(DEV))
+    want = orc.logmel_f32_port_per_utterance(torch.from_numpy(clips), 80)
+    for i in range(len(clips)):
+        assert _maxerr(got[i], want[i]) <= TOL, (i, _maxerr(got[i], want[i]))
+    # the same clips shuffled inside a larger batch give the same bytes
+    big = np.concatenate([clips[::-1], clips, clips[2:3]])
+    again = b200.log_mel_spectrogram_batch(torch.from_numpy(big).to(DEV))
+    assert torch.equal(again[5:10], got) and torch.equal(again[10], got[2])
+
+
 def test_pcm16_ingest_is_bit_equal_to_the_float_path(b200):
     q = np.stack([signals.make_pcm16(32000, 60 + i) for i in range(4)])
     f = q.astype(np.float32) / 32768.0  # audio.py:62
