@@ -301,6 +301,11 @@ def run_own_arm(args) -> None:
     norm_ms, norm_launches = prof["normalise"]
     algo_bytes_step = B * bytes_per_clip(n_mels)
     achieved = algo_bytes_step * args.steps / (fused_ms / 1e3) / 1e9 if fused_ms > 0 else None
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
+    traffic, traffic_source = args.traffic_bytes, "--traffic-bytes" if args.traffic_bytes else None
+    if traffic is None and fused_kind == "tcgen05_pass" and n_mels == 80 and B == DEFAULT_BATCH:
+        traffic = 492.488448e6 + 214.921472e6
+        traffic_source = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_tc_final_ncu_full_summary.txt)"
     roofline = {
         "bound": "hbm",
         "kernel": f"logmel_{fused_kind}",
@@ -308,7 +313,8 @@ def run_own_arm(args) -> None:
         "peak": peak_gbs,
         "unit": "GB/s",
         "frac": achieved / peak_gbs if achieved else None,
-        "traffic": args.traffic_bytes,
+        "traffic": traffic,
+        "traffic_source": traffic_source,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": algo_bytes_step * args.steps / max(fused_launches, 1),
         "kernel_ms_per_launch": fused_ms / max(fused_launches, 1),
