@@ -284,6 +284,27 @@ __device__ __forceinline__ TileCoord tile_coord(int64_t tile, int tiles_per_clip
     c.t0 = static_cast<int>(tile - c.clip * tiles_per_clip) * kTcTileFrames;
     return c;
 }
+// A CTA's tiles are blockIdx.x, + gridDim.x, ...: walking them needs one division up front, then adds only (the
+// 64-bit division is ~100 instructions, and every role that walks the tiles would carry a copy in its hot loop).
+struct TileCursor {
+    TileCoord at;
+    int step_clips, step_t0, frames_per_clip;   // gridDim.x tiles = step_clips whole utterances + step_t0 frames
+    __device__ __forceinline__ TileCursor(int tiles_per_clip) {
+        const unsigned first = blockIdx.x, tpc = static_cast<unsigned>(tiles_per_clip), grid = gridDim.x;
+        at.clip = first / tpc;
+        at.t0 = static_cast<int>(first % tpc) * kTcTileFrames;
+        step_clips = static_cast<int>(grid / tpc);
+        step_t0 = static_cast<int>(grid % tpc) * kTcTileFrames;
+        frames_per_clip = tiles_per_clip * kTcTileFrames;
+    }
+    __device__ __forceinline__ TileCoord peek_next() const {
+        TileCoord n = at;
+        n.clip += step_clips; n.t0 += step_t0;
+        if (n.t0 >= frames_per_clip) { n.t0 -= frames_per_clip; ++n.clip; }
+        return n;
+    }
+    __device__ __forceinline__ void advance() { at = peek_next(); }
+};
 
 // ---- loaders: one tile of audio into shared memory -----------------------------------------------
 // The tile is 130 rows of 160 samples (one contiguous span of the utterance) at pitch 164 words.
@@ -448,6 +469,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
     uint32_t old_max = 0, old_min = 0, old_tile_max = 0, old_tile_min = 0;
     const int64_t my_tiles = static_cast<int64_t>(blockIdx.x) < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TileCoord prev{0, 0};
+    TileCursor cursor(tiles_per_clip);
     // One pass per tile plus a last pass that only finishes the final tile.  A tile is FINISHED (log10, stores,
     // extremes) after unit 0 of the next tile has been pulled out of the accumulator, so the tensor cores run the next
     // unit while the stores go out; unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep).
@@ -550,7 +572,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
             else tc_epilogue_unit<NM, 1, HALF>(d, acc);
             if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
         }
-        if (more) prev = tile_coord(blockIdx.x + k * gridDim.x, tiles_per_clip);
+        if (more) { prev = cursor.at; cursor.advance(); }
     }
     // the last tile is counted behind an unconditional fence; after it every row of this warp is visible
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -642,11 +664,12 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         const float* fr = s_audio + (quad * 32 + lane) * kTcRowPitch;
         uint32_t parity = 0;
         int ti = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        TileCursor cursor(tiles_per_clip);
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, cursor.advance()) {
             if (quad == 0) TC_TRACE(1 + sweep, ti, 0);
             if (trace != nullptr && blockIdx.x == 0 && tid == 0 && ti < kTileStamps)
                 trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + ti] = clock64();
-            const TileCoord tcl = tile_coord(tile, tiles_per_clip);
+            const TileCoord tcl = cursor.at;
             if (tile_uses_tma<InT>(a, tma_rows, tcl)) {
                 if (lane == 0) mbar_arrive(&bars.audio_full);   // the loader warp brings this tile
             } else {
@@ -721,18 +744,18 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
             // ===== loader warp =====
             // Ask L2 for a tile one tile period before it is copied: the CTAs of a wave load in lock-step, so without
             // the prefetch every staging phase waits on an HBM burst while HBM idles the rest of the time.
-            auto prefetch = [&](int64_t tile) {
-                const TileCoord tp = tile_coord(tile, tiles_per_clip);
+            auto prefetch = [&](const TileCoord& tp) {
                 if (tile_uses_tma<InT>(a, tma_rows, tp)) tma_prefetch_tile(&audio_map, tp);
                 else prefetch_tile_l2<InT>(a, tp);
             };
-            if (lane == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) prefetch(blockIdx.x);
+            TileCursor cursor(tiles_per_clip);
+            if (lane == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) prefetch(cursor.at);
             uint32_t parity = 1;   // audio_empty: the first wait passes
             int ti = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, cursor.advance()) {
                 TC_TRACE(0, ti, 0);
-                if (lane == 0 && tile + gridDim.x < total_tiles) prefetch(tile + gridDim.x);
-                const TileCoord tcl = tile_coord(tile, tiles_per_clip);
+                if (lane == 0 && tile + gridDim.x < total_tiles) prefetch(cursor.peek_next());
+                const TileCoord tcl = cursor.at;
                 const bool tma = tile_uses_tma<InT>(a, tma_rows, tcl);
                 mbar_wait(&bars.audio_empty, parity);           // every fold warp has finished reading the previous tile
                 parity ^= 1u;

@@ -445,9 +445,9 @@ template <int NM> struct TcEpilogueLayout {
     static_assert(straddle >= 0 && straddle <= 3, "unexpected mel layout around the split");
 };
 
-// one accumulator column: d = D[frame][k'] of unit U; adds w * d^2 to the (<= 2) mels of its bin
+// one accumulator column: t = D[frame][k']^2 of unit U; adds w * t to the (<= 2) mels of its bin
 template <int NM, int U, int HALF, int C, int ACC>
-B200_HD void tc_epilogue_col(float d, float (&acc)[ACC]) {
+B200_HD void tc_epilogue_col(float t, float (&acc)[ACC]) {
     using L = TcEpilogueLayout<NM>;
     constexpr int kp = L::col0(HALF) + C;
     if constexpr (kp < kTcBinsPerUnit) {
@@ -458,23 +458,49 @@ B200_HD void tc_epilogue_col(float d, float (&acc)[ACC]) {
             static_assert(m0 >= 0 && m0 + cnt <= ACC, "bin outside the half's mel range");
             constexpr float w0 = MelBands<NM>::bin_weight[bin][0] * kTcPowerUnscale;   // FFMA immediates
             constexpr float w1 = MelBands<NM>::bin_weight[bin][1] * kTcPowerUnscale;
-            const float t = d * d;
             acc[m0] = fmaf(w0, t, acc[m0]);
             if constexpr (cnt == 2) acc[m0 + 1] = fmaf(w1, t, acc[m0 + 1]);
         }
     }
 }
+template <int NM, int U, int HALF, int C> B200_HD constexpr bool tc_col_used() {
+    constexpr int kp = TcEpilogueLayout<NM>::col0(HALF) + C;
+    if constexpr (kp < kTcBinsPerUnit) return tc_bin_count<NM>(tc_unit_bin(U, kp)) > 0;
+    else return false;
+}
 
-template <int NM, int U, int HALF, int ACC, int NCOLS, int... C>
-B200_HD void tc_epilogue_cols(const float (&d)[NCOLS], float (&acc)[ACC], std::integer_sequence<int, C...>) {
-    (tc_epilogue_col<NM, U, HALF, C, ACC>(d[C], acc), ...);
+// two neighbouring columns: the squares are one packed multiply (FMUL2) on the register pair tcgen05.ld delivered
+template <int NM, int U, int HALF, int P, int ACC, int NCOLS>
+B200_HD void tc_epilogue_pair(const float (&d)[NCOLS], float (&acc)[ACC]) {
+    constexpr int C = 2 * P;
+    constexpr bool use_a = tc_col_used<NM, U, HALF, C>(), use_b = tc_col_used<NM, U, HALF, C + 1>();
+    if constexpr (use_a && use_b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+        const float2 v = make_float2(d[C], d[C + 1]);
+        const float2 t = __fmul2_rn(v, v);
+        tc_epilogue_col<NM, U, HALF, C, ACC>(t.x, acc);
+        tc_epilogue_col<NM, U, HALF, C + 1, ACC>(t.y, acc);
+#else
+        tc_epilogue_col<NM, U, HALF, C, ACC>(d[C] * d[C], acc);
+        tc_epilogue_col<NM, U, HALF, C + 1, ACC>(d[C + 1] * d[C + 1], acc);
+#endif
+    } else {
+        if constexpr (use_a) tc_epilogue_col<NM, U, HALF, C, ACC>(d[C] * d[C], acc);
+        if constexpr (use_b) tc_epilogue_col<NM, U, HALF, C + 1, ACC>(d[C + 1] * d[C + 1], acc);
+    }
+}
+
+template <int NM, int U, int HALF, int ACC, int NCOLS, int... P>
+B200_HD void tc_epilogue_cols(const float (&d)[NCOLS], float (&acc)[ACC], std::integer_sequence<int, P...>) {
+    (tc_epilogue_pair<NM, U, HALF, P, ACC, NCOLS>(d, acc), ...);
 }
 
 // all columns of one half of unit U (d[c] = accumulator column col0(HALF) + c)
 template <int NM, int U, int HALF, int ACC, int NCOLS>
 B200_HD void tc_epilogue_unit(const float (&d)[NCOLS], float (&acc)[ACC]) {
     static_assert(NCOLS == TcEpilogueLayout<NM>::cols(HALF) && ACC == TcEpilogueLayout<NM>::acc_size(HALF), "half shape");
-    tc_epilogue_cols<NM, U, HALF, ACC, NCOLS>(d, acc, std::make_integer_sequence<int, NCOLS>{});
+    static_assert(NCOLS % 2 == 0, "columns are processed in pairs");
+    tc_epilogue_cols<NM, U, HALF, ACC, NCOLS>(d, acc, std::make_integer_sequence<int, NCOLS / 2>{});
 }
 
 }  // namespace b200mel
