@@ -208,6 +208,18 @@ B200_HD float log10_clamped(float s) {
 #endif
 }
 
+// log2(max(S, 1e-10)): log10_clamped before its final scaling (for callers that scale two values with one FMUL2).
+B200_HD float log2_clamped(float s) {
+    s = max_nan(s, 1e-10f);
+#if defined(__CUDA_ARCH__)
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(s));
+    return l2;
+#else
+    return __builtin_log2f(s);
+#endif
+}
+
 // Final dynamic-range clamp and affine map of audio.py:155-156.
 B200_HD float normalise(float lg, float gmax) {
     if (gmax != gmax) return gmax;  // NaN max poisons the whole call, as in torch

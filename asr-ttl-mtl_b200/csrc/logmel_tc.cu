@@ -426,16 +426,19 @@ __device__ __forceinline__ void sweep_store(int sweep, const float* fr, uint32_t
     uint32_t c = lane_addr + (sweep == 0 ? tc_hi_col(0) : tc_hi_col(2));   // hi block of the sweep's first unit
     uint32_t hf[4], lf[4], hs[4], ls[4];
 #pragma unroll 1
-    for (int j = 0; j < 2 * kTcMainSteps; ++j, c += 4) {                   // slots 8j..8j+7 of the main blocks
+    for (int j = 0; j < kTcChunks; ++j, c += 4) {
         tc_sweep_chunk_row(fr, rows[j], sign, head, hf, lf, hs, ls);
-        tmem_st4(c, hf); tmem_st4(c + 48, lf);                             // unit: [hi 48 | lo 48], next unit 96 columns on
-        tmem_st4(c + 96, hs); tmem_st4(c + 144, ls);
+        if (j < 2 * kTcMainSteps) {                                        // slots 8j..8j+7 of the main blocks
+            tmem_st4(c, hf); tmem_st4(c + 48, lf);                         // unit: [hi 48 | lo 48], next unit 96 columns on
+            tmem_st4(c + 96, hs); tmem_st4(c + 144, ls);
+        } else {
+            // slots 96..101 (same loop body, its own store pattern): [hi x 3 | lo x 3] columns of the leftover area,
+            // second unit 6 columns on
+            const uint32_t b1 = lane_addr + (sweep == 0 ? tc_left_col(0) : tc_left_col(2)), b2 = b1 + 6;
+            tmem_st2(b1, hf[0], hf[1]); tmem_st2(b1 + 2, hf[2], lf[0]); tmem_st2(b1 + 4, lf[1], lf[2]);
+            tmem_st2(b2, hs[0], hs[1]); tmem_st2(b2 + 2, hs[2], ls[0]); tmem_st2(b2 + 4, ls[1], ls[2]);
+        }
     }
-    tc_sweep_chunk_row(fr, rows[2 * kTcMainSteps], sign, head, hf, lf, hs, ls);
-    // slots 96..101: [hi x 3 | lo x 3] columns of the leftover area, second unit 6 columns on
-    const uint32_t b1 = lane_addr + (sweep == 0 ? tc_left_col(0) : tc_left_col(2)), b2 = b1 + 6;
-    tmem_st2(b1, hf[0], hf[1]); tmem_st2(b1 + 2, hf[2], lf[0]); tmem_st2(b1 + 4, lf[1], lf[2]);
-    tmem_st2(b2, hs[0], hs[1]); tmem_st2(b2 + 2, hs[2], ls[0]); tmem_st2(b2 + 4, ls[1], ls[2]);
 }
 static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) == 96 && tc_hi_col(3) - tc_hi_col(2) == 96 &&
               tc_left_col(1) - tc_left_col(0) == 6 && tc_left_col(3) - tc_left_col(2) == 6, "column arithmetic of sweep_store");
@@ -532,8 +535,22 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                 if (live) {
                     const float scale = a.fused_norm ? 0.25f : 1.0f, shift = a.fused_norm ? 1.0f : 0.0f;
                     const uint32_t pitch32 = static_cast<uint32_t>(a.n_frames);
+                    // two mels per step: log2 on the MUFU, then log10 scaling and the affine map as packed FMUL2 / FFMA2
+                    // (the same two roundings per value as the scalar form)
+                    constexpr float kLog10Of2 = 0.30102999566398120f;
+                    const float2 scale2 = make_float2(scale, scale), shift2 = make_float2(shift, shift);
 #pragma unroll
-                    for (int m = m_begin; m < m_end; ++m) {
+                    for (int m = m_begin; m + 1 < m_end; m += 2) {
+                        const float2 l2 = make_float2(log2_clamped(acc[m - L::acc_base(HALF)]), log2_clamped(acc[m + 1 - L::acc_base(HALF)]));
+                        const float2 lg = __fmul2_rn(l2, make_float2(kLog10Of2, kLog10Of2));
+                        const float2 y = __ffma2_rn(lg, scale2, shift2);
+                        out[static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin)] = y.x;
+                        out[static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1 - m_begin)] = y.y;
+                        mx = max_nan(mx, max_nan(lg.x, lg.y));
+                        mn = fminf(mn, fminf(lg.x, lg.y));
+                    }
+                    if constexpr ((m_end - m_begin) % 2 == 1) {
+                        constexpr int m = m_end - 1;
                         const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
                         out[static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin)] = fmaf(lg, scale, shift);
                         mx = max_nan(mx, lg);
