@@ -473,13 +473,15 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
     const int64_t my_tiles = static_cast<int64_t>(blockIdx.x) < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TileCoord prev{0, 0};
     TileCursor cursor(tiles_per_clip);
-    // One pass per tile plus a last pass that only finishes the final tile.  A tile is FINISHED (log10, stores,
-    // extremes) after unit 0 of the next tile has been pulled out of the accumulator, so the tensor cores run the next
-    // unit while the stores go out; unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep).
+    // Unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep).  A tile is FINISHED (log10, stores, extremes) right
+    // after its last unit: the tensor cores then wait for the next tile's E operand anyway, and unit 0 of the next tile
+    // runs while the stores go out (tools/pipeline_model.py: better than finishing after the next tile's unit 0).
 #pragma unroll 1
-    for (int64_t k = 0; k <= my_tiles; ++k) {
-        const bool more = k < my_tiles;
+    for (int64_t k = 0; k < my_tiles; ++k) {
+        constexpr bool more = true;
         const int ti = static_cast<int>(k);
+        prev = cursor.at;
+        cursor.advance();
 #pragma unroll 1
         for (int u = 0; u < kTcUnits; ++u) {
             float d[L::cols(HALF)];
@@ -495,8 +497,13 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                 if (lane == 0) mbar_arrive(&bars->d_empty);   // the accumulator is in registers: the next unit may overwrite it
                 if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 1);
             }
-            if (u == 0 && k > 0) {
-                // ---- finish the previous tile ----
+            // Re and Im of a bin take the same weights: units 0 / 2 (even bins) share one body, units 1 / 3 (odd bins) the other
+            if (debug_stage == 4) acc[0] += d[0] + d[L::cols(HALF) - 1];   // bring-up: loads only
+            else if ((u & 1) == 0) tc_epilogue_unit<NM, 0, HALF>(d, acc);
+            else tc_epilogue_unit<NM, 1, HALF>(d, acc);
+            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
+            if (u == kTcUnits - 1) {
+                // ---- finish this tile ----
                 if (pending_clip >= 0) {                       // count the tile before it
                     const bool fence = *slow_mode != 0;
                     if (fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -504,11 +511,11 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                     __syncwarp();
                     if (lane == 0) {
                         atomicAdd(a.done_counters + pending_clip, 1u);
-                        if (fence) *reinterpret_cast<volatile uint32_t*>(&norm->fenced_below[me]) = static_cast<uint32_t>(k - 1);
+                        if (fence) *reinterpret_cast<volatile uint32_t*>(&norm->fenced_below[me]) = static_cast<uint32_t>(k);
                     }
                     pending_clip = -1;
                 }
-                if (quad == 0) TC_TRACE(4 + HALF, ti - 1, 13);
+                if (quad == 0) TC_TRACE(4 + HALF, ti, 13);
                 // join the mels that straddle the split: half 1 hands its partial sums to half 0
                 float* strad = s_straddle + ((buf * 4 + quad) * 3) * 32 + lane;
                 if constexpr (HALF == 1) {
@@ -521,7 +528,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                     for (int j = 0; j < L::straddle; ++j) acc[L::high_base + j] += strad[j * 32];
                 }
                 buf ^= 1u;
-                if (quad == 0) TC_TRACE(4 + HALF, ti - 1, 14);
+                if (quad == 0) TC_TRACE(4 + HALF, ti, 14);
                 // log10 clamp, coalesced row stores (lane = frame), utterance extremes
                 const int f = quad * 32 + lane, t = prev.t0 + f;
                 const bool live = t < a.n_frames;
@@ -559,7 +566,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                 }
 #pragma unroll
                 for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
-                if (quad == 0) TC_TRACE(4 + HALF, ti - 1, 15);
+                if (quad == 0) TC_TRACE(4 + HALF, ti, 15);
                 uint32_t key = live ? max_key_encode(mx) : 0u;
                 key = __reduce_max_sync(0xffffffffu, key);
                 if (a.fused_norm) {
@@ -569,7 +576,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                         old_max = atomicMax(a.max_keys + (a.global_max ? 0 : prev.clip), key);
                         old_min = atomicMax(a.min_keys + prev.clip, inv);
                         if (a.tile_keys != nullptr) {   // the tile's own extremes: lets the clamp path skip or fill whole tiles
-                            uint32_t* tk = a.tile_keys + 2 * (static_cast<int64_t>(blockIdx.x) + (k - 1) * gridDim.x);
+                            uint32_t* tk = a.tile_keys + 2 * (static_cast<int64_t>(blockIdx.x) + k * gridDim.x);
                             old_tile_max = atomicMax(tk, key);
                             old_tile_min = atomicMax(tk + 1, inv);
                         }
@@ -578,18 +585,11 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                 } else if (lane == 0) {
                     atomicMax(a.max_keys + (a.global_max ? 0 : prev.clip), key);
                 }
-                if (quad == 0) TC_TRACE(4 + HALF, ti - 1, 12);
-                if (HALF == 0 && trace != nullptr && blockIdx.x == 0 && quad == 0 && lane == 0 && ti - 1 < kTileStamps)
-                    trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + kTileStamps + ti - 1] = clock64();
+                if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
+                if (HALF == 0 && trace != nullptr && blockIdx.x == 0 && quad == 0 && lane == 0 && ti < kTileStamps)
+                    trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + kTileStamps + ti] = clock64();
             }
-            if (!more) break;
-            // Re and Im of a bin take the same weights: units 0 / 2 (even bins) share one body, units 1 / 3 (odd bins) the other
-            if (debug_stage == 4) acc[0] += d[0] + d[L::cols(HALF) - 1];   // bring-up: loads only
-            else if ((u & 1) == 0) tc_epilogue_unit<NM, 0, HALF>(d, acc);
-            else tc_epilogue_unit<NM, 1, HALF>(d, acc);
-            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
         }
-        if (more) { prev = cursor.at; cursor.advance(); }
     }
     // the last tile is counted behind an unconditional fence; after it every row of this warp is visible
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
