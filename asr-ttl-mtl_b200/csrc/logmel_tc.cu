@@ -415,18 +415,20 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
 // ---- fold warps: one sweep of one tile, A operand -> tensor memory -----------------------------------
 __constant__ TcFoldRows c_fold_rows = tc_make_fold_rows();
 
-// One compact loop for both sweeps (see TcFoldRows): 12 main chunks, then the leftover chunk with its own store
-// pattern.  `sweep` is warp-uniform, so the table rows arrive through the uniform datapath.
-__device__ __forceinline__ void sweep_store(int sweep, const float* fr, uint32_t lane_addr) {
+// One compact loop for both sweeps (see TcFoldRows), run over the chunks [j0, j1): the two fold warps of a lane
+// quadrant split every sweep between them (chunks 0..6 and 7..12), so a sweep's operand is complete in half the time
+// and the tensor cores start on it that much earlier.  Chunk 12 is the leftover chunk with its own store pattern.
+// `sweep` is warp-uniform, so the table rows arrive through the uniform datapath.
+__device__ __forceinline__ void sweep_store(int sweep, int j0, int j1, const float* fr, uint32_t lane_addr) {
     const TcFoldRow* __restrict__ rows = c_fold_rows.row[sweep];
     const float sign = c_fold_rows.sign[sweep];
     float head[2];
-    head[0] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(fr) + c_fold_rows.head[sweep][0]);
-    head[1] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(fr) + c_fold_rows.head[sweep][1]);
-    uint32_t c = lane_addr + (sweep == 0 ? tc_hi_col(0) : tc_hi_col(2));   // hi block of the sweep's first unit
+    head[0] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(fr) + rows[j0].head[0]);
+    head[1] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(fr) + rows[j0].head[1]);
+    uint32_t c = lane_addr + (sweep == 0 ? tc_hi_col(0) : tc_hi_col(2)) + 4 * j0;   // hi block of the sweep's first unit
     uint32_t hf[4], lf[4], hs[4], ls[4];
 #pragma unroll 1
-    for (int j = 0; j < kTcChunks; ++j, c += 4) {
+    for (int j = j0; j < j1; ++j, c += 4) {
         tc_sweep_chunk_row(fr, rows[j], sign, head, hf, lf, hs, ls);
         if (j < 2 * kTcMainSteps) {                                        // slots 8j..8j+7 of the main blocks
             tmem_st4(c, hf); tmem_st4(c + 48, lf);                         // unit: [hi 48 | lo 48], next unit 96 columns on
@@ -440,6 +442,7 @@ __device__ __forceinline__ void sweep_store(int sweep, const float* fr, uint32_t
         }
     }
 }
+constexpr int kFoldSplit = 7;   // chunks [0, 7) and [7, 13)
 static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) == 96 && tc_hi_col(3) - tc_hi_col(2) == 96 &&
               tc_left_col(1) - tc_left_col(0) == 6 && tc_left_col(3) - tc_left_col(2) == 6, "column arithmetic of sweep_store");
 
@@ -643,7 +646,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     if (tid == 32) {
         mbar_init(&bars.audio_full, 9);
         mbar_init(&bars.audio_empty, 8);
-        mbar_init(&bars.a_full[0], 4); mbar_init(&bars.a_full[1], 4);
+        mbar_init(&bars.a_full[0], 8); mbar_init(&bars.a_full[1], 8);
         mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
         mbar_init(&bars.d_full, 1);
         mbar_init(&bars.d_empty, 8);
@@ -676,14 +679,14 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     // (a setmaxnreg.inc can only take what another warpgroup released): folds 80 + 80, epilogue 144 + 144, rest 32
     if (warp < kWarpEpi0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        // ===== fold warps: E sweep (warps 0-3) / O sweep (warps 4-7) =====
-        const int sweep = warp < kWarpO ? 0 : 1;
+        // ===== fold warps: two per lane quadrant; both do half of the E sweep, then half of the O sweep =====
+        const int part = warp < kWarpO ? 0 : 1;
         const float* fr = s_audio + (quad * 32 + lane) * kTcRowPitch;
         uint32_t parity = 0;
         int ti = 0;
         TileCursor cursor(tiles_per_clip);
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, cursor.advance()) {
-            if (quad == 0) TC_TRACE(1 + sweep, ti, 0);
+            if (quad == 0) TC_TRACE(1 + part, ti, 0);
             if (trace != nullptr && blockIdx.x == 0 && tid == 0 && ti < kTileStamps)
                 trace[kTraceRoles * kTraceTiles * kTraceEvents + 6 * kStampCtas + ti] = clock64();
             const TileCoord tcl = cursor.at;
@@ -694,17 +697,25 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 produce_tile<InT>(a, tcl, s_audio, &bars.audio_full, tid);
             }
             mbar_wait(&bars.audio_full, parity);
-            if (quad == 0) TC_TRACE(1 + sweep, ti, 1);
-            mbar_wait(&bars.a_empty[sweep], parity ^ 1u);   // the tensor cores are done with the previous tile's operand
-            if (quad == 0) TC_TRACE(1 + sweep, ti, 2);
-            tc_fence_after();
-            sweep_store(sweep, fr, lane_addr);
-            if (quad == 0) TC_TRACE(1 + sweep, ti, 3);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&bars.audio_empty); mbar_arrive(&bars.a_full[sweep]); }
-            if (quad == 0) TC_TRACE(1 + sweep, ti, 4);
+            if (quad == 0) TC_TRACE(1 + part, ti, 1);
+#pragma unroll 1
+            for (int sweep = 0; sweep < 2; ++sweep) {
+                mbar_wait(&bars.a_empty[sweep], parity ^ 1u);   // the tensor cores are done with the previous tile's operand
+                if (quad == 0) TC_TRACE(1 + part, ti, 2 + 3 * sweep);
+                tc_fence_after();
+                // warp `part` takes the first chunks of the E sweep and the last ones of the O sweep (7 + 6 either way)
+                const bool first_half = (part == 0) == (sweep == 0);
+                sweep_store(sweep, first_half ? 0 : kFoldSplit, first_half ? kFoldSplit : kTcChunks, fr, lane_addr);
+                if (quad == 0) TC_TRACE(1 + part, ti, 3 + 3 * sweep);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (sweep == 1) mbar_arrive(&bars.audio_empty);
+                    mbar_arrive(&bars.a_full[sweep]);
+                }
+                if (quad == 0) TC_TRACE(1 + part, ti, 4 + 3 * sweep);
+            }
             parity ^= 1u;
         }
     } else if (warp < kWarpMma) {

@@ -324,10 +324,11 @@ B200_HD void tc_sweep_chunk_ct(const float* fr, const TcFoldWeights& w, float (&
 struct TcFoldRow {
     int group[8];            // byte offsets: run 0 ascending a, b; run 0 descending a, b; run 1 ascending a, b; run 1 descending a, b
     float wa[8], wb[8];      // 256 w[n], +-256 w[200-n] per slot (0 for slots without a tap)
+    int head[2];             // byte offset of the first (highest) sample of each descending run: where a warp that STARTS
+    int pad[2];              // at this chunk finds what the previous chunk would have handed on
 };
 struct TcFoldRows {
     TcFoldRow row[2][kTcChunks];
-    int head[2][2];          // byte offset of the first (highest) sample of each descending run of chunk 0
     float sign[2];           // +1 (E sweep), -1 (O sweep)
 };
 constexpr TcFoldRows tc_make_fold_rows() {
@@ -350,9 +351,10 @@ constexpr TcFoldRows tc_make_fold_rows() {
                 r.wa[i] = live ? kTcWindow.v[n] : 0.0f;
                 r.wb[i] = live ? (sweep == 0 ? kTcWindow.v[200 - n] : -kTcWindow.v[200 - n]) : 0.0f;
             }
+            for (int q = 0; q < 2; ++q)      // x[400] (E chunk 0, weight 0): any in-frame sample
+                r.head[q] = 4 * tc_off(D[q] > 399 ? 0 : (D[q] < 0 ? 0 : D[q]));
+            r.pad[0] = r.pad[1] = 0;
         }
-        t.head[sweep][0] = 4 * tc_off(sweep == 0 ? 0 : 100);
-        t.head[sweep][1] = 4 * tc_off(sweep == 0 ? 200 : 300);
         t.sign[sweep] = sweep == 0 ? 1.0f : -1.0f;
     }
     return t;

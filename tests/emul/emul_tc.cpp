@@ -68,7 +68,12 @@ void chunk_to_tmem(const float* fr, float (&head)[2], uint32_t* lane) {
             if (hf[q] != hf2[q] || lf[q] != lf2[q] || hs[q] != hs2[q] || ls[q] != ls2[q]) g_chunk_mismatch = 1;
     }
     {   // ... and so must the row-driven form the kernel runs (its own head carry, checked chunk by chunk)
-        if (J == 0) { head_row[SWEEP][0] = fr[kFoldRows.head[SWEEP][0] / 4]; head_row[SWEEP][1] = fr[kFoldRows.head[SWEEP][1] / 4]; }
+        // a warp may start a sweep at any chunk (the kernel's two warps per quadrant start at chunks 0 and 7): the row's
+        // own head offsets must give what the carry would have
+        if (J == 0) { head_row[SWEEP][0] = fr[kFoldRows.row[SWEEP][0].head[0] / 4]; head_row[SWEEP][1] = fr[kFoldRows.row[SWEEP][0].head[1] / 4]; }
+        else if (J < kTcChunks - 1 &&
+                 (head_row[SWEEP][0] != fr[kFoldRows.row[SWEEP][J].head[0] / 4] || head_row[SWEEP][1] != fr[kFoldRows.row[SWEEP][J].head[1] / 4]))
+            g_chunk_mismatch = 1;
         uint32_t hf3[4], lf3[4], hs3[4], ls3[4];
         tc_sweep_chunk_row(fr, kFoldRows.row[SWEEP][J], kFoldRows.sign[SWEEP], head_row[SWEEP], hf3, lf3, hs3, ls3);
         const int live = J < 2 * kTcMainSteps ? 4 : 3;
