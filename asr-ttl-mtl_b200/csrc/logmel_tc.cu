@@ -207,6 +207,7 @@ static_assert(kSmemAudio % 128 == 0 && kSmemBytes <= 227 * 1024, "shared memory 
 
 struct TcBarriers {
     uint64_t audio_full, audio_empty;
+    uint64_t tma_done;                // tiles whose edge rows the loader patches after the tensor copy has landed
     uint64_t a_full[2], a_empty[2];   // [E sweep, O sweep]
     uint64_t d_full, d_empty;
 };
@@ -351,13 +352,63 @@ __device__ __forceinline__ void prefetch_tile_l2(const LogmelArgs& a, const Tile
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(begin), "r"(static_cast<uint32_t>(end - begin)) : "memory");
 }
 
-// whether the TMA unit brings this tile (same answer in the loader warp and in the fold warps)
+// whether the TMA unit brings this tile (same answer in the loader warp and in the fold warps):
+//   - every row of the tile lies inside the utterance's valid samples, or
+//   - the utterance is valid to its last sample in memory (no `lengths` cut): the TMA unit zero-fills the rows it cannot
+//     address (before the first sample, past the last whole row) and the loader warp then rewrites the one to three of
+//     them that hold real or reflected samples (patch_tile_edges) - so the tiles at a clip's two ends need no other path
 template <typename InT>
 __device__ __forceinline__ bool tile_uses_tma(const LogmelArgs& a, int tma_rows, const TileCoord& tc) {
     if constexpr (sizeof(InT) != 4) return false;
-    if (tma_rows <= 0 || tc.t0 < kTmaLeadRows || tc.t0 - kTmaLeadRows + kTcAudioRows > tma_rows) return false;
-    return static_cast<int64_t>(tc.t0) * kHop - kHalfWin + kTcAudioSamples <= valid_samples(a, tc.clip);
+    if (tma_rows <= 0) return false;
+    const int64_t valid = valid_samples(a, tc.clip);
+    if (valid == a.n_samples) return true;
+    if (tc.t0 < kTmaLeadRows || tc.t0 - kTmaLeadRows + kTcAudioRows > tma_rows) return false;
+    return static_cast<int64_t>(tc.t0) * kHop - kHalfWin + kTcAudioSamples <= valid;
 }
+// tile row r holds positions p0 = 160 (t0 + r) - 200 ...; the TMA unit zero-filled it if its tensor row is out of range
+__device__ __forceinline__ bool tile_row_needs_patch(const LogmelArgs& a, int tma_rows, const TileCoord& tc, int r) {
+    const int c2 = tc.t0 - kTmaLeadRows + r;
+    if (c2 >= 0 && c2 < tma_rows) return false;
+    const int64_t p0 = static_cast<int64_t>(tc.t0 + r) * kHop - kHalfWin;
+    if (p0 >= a.total + kHalfWin) return false;                                  // beyond the reflected tail: zeros
+    if (p0 >= a.n_samples && a.n_samples + kHalfWin < a.total) return false;      // inside a long zero padding: zeros
+    return true;
+}
+__device__ __forceinline__ bool tile_needs_patch(const LogmelArgs& a, int tma_rows, const TileCoord& tc) {
+    const int c2_first = tc.t0 - kTmaLeadRows;
+    return c2_first < 0 || c2_first + kTcAudioRows > tma_rows;     // (a superset test; the row test decides)
+}
+// the loader warp rewrites the zero-filled rows that hold real or reflected samples (5 samples per lane and row)
+__device__ __forceinline__ void patch_tile_edges(const LogmelArgs& a, int tma_rows, const TileCoord& tc, float* s_audio, int lane) {
+    const float* __restrict__ row = static_cast<const float*>(a.audio) + tc.clip * a.stride_b;
+    // candidates: the rows before tensor row 0 (at most two, in a clip's first tile) and the rows from the first tensor
+    // row past the end up to the end of the reflected tail (at most three)
+    const int c2_first = tc.t0 - kTmaLeadRows;
+    const int r_past = tma_rows - c2_first < 0 ? 0 : tma_rows - c2_first;
+#pragma unroll 1
+    for (int i = 0; i < kTmaLeadRows + 4; ++i) {
+        const int r = i < kTmaLeadRows ? i : r_past + (i - kTmaLeadRows);
+        if (r >= kTcAudioRows || (i >= kTmaLeadRows && r < kTmaLeadRows && c2_first < 0 && r + c2_first < 0)) continue;   // (no row twice)
+        if (!tile_row_needs_patch(a, tma_rows, tc, r)) continue;
+        const int64_t p0 = static_cast<int64_t>(tc.t0 + r) * kHop - kHalfWin;
+        float* dst = s_audio + r * kTcRowPitch;
+        // all five loads of the lane are issued before any is used (one L2 round trip per row, not five)
+        float v[kHop / 32];
+        bool real[kHop / 32];
+#pragma unroll
+        for (int k = 0; k < kHop / 32; ++k) {
+            const int64_t pos = p0 + lane + 32 * k;
+            int64_t idx = reflect_source_index(pos, a.total);
+            real[k] = pos < a.total + kHalfWin && idx >= 0 && idx < a.n_samples;
+            idx = real[k] ? idx : 0;
+            v[k] = __ldg(row + idx);
+        }
+#pragma unroll
+        for (int k = 0; k < kHop / 32; ++k) dst[lane + 32 * k] = real[k] ? v[k] : 0.f;
+    }
+}
+
 __device__ __forceinline__ void tma_load_tile(const CUtensorMap* map, const TileCoord& tc, float* s_audio, uint64_t* full) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(full)), "r"(kTmaTileBytes) : "memory");
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -646,6 +697,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     if (tid == 32) {
         mbar_init(&bars.audio_full, 9);
         mbar_init(&bars.audio_empty, 8);
+        mbar_init(&bars.tma_done, 1);
         mbar_init(&bars.a_full[0], 8); mbar_init(&bars.a_full[1], 8);
         mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
         mbar_init(&bars.d_full, 1);
@@ -779,6 +831,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
             TileCursor cursor(tiles_per_clip);
             if (lane == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) prefetch(cursor.at);
             uint32_t parity = 1;   // audio_empty: the first wait passes
+            uint32_t patch_parity = 0;
             int ti = 0;
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, cursor.advance()) {
                 TC_TRACE(0, ti, 0);
@@ -788,7 +841,16 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 mbar_wait(&bars.audio_empty, parity);           // every fold warp has finished reading the previous tile
                 parity ^= 1u;
                 TC_TRACE(0, ti, 1);
-                if (lane == 0) {
+                if (tma && tile_needs_patch(a, tma_rows, tcl)) {
+                    // a clip's first or last tile: the copy completes on a private barrier, then the edge rows are rewritten
+                    if (lane == 0) tma_load_tile(&audio_map, tcl, s_audio, &bars.tma_done);
+                    mbar_wait(&bars.tma_done, patch_parity);
+                    patch_parity ^= 1u;
+                    TC_TRACE(0, ti, 3);
+                    patch_tile_edges(a, tma_rows, tcl, s_audio, lane);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.audio_full);
+                } else if (lane == 0) {
                     if (tma) tma_load_tile(&audio_map, tcl, s_audio, &bars.audio_full);
                     else mbar_arrive(&bars.audio_full);         // cooperative mode: the fold warps bring the tile
                 }
