@@ -304,7 +304,7 @@ def run_own_arm(args) -> None:
     # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
     traffic, traffic_source = args.traffic_bytes, "--traffic-bytes" if args.traffic_bytes else None
     if traffic is None and fused_kind == "tcgen05_pass" and n_mels == 80 and B == DEFAULT_BATCH:
-        traffic = 492.193024e6 + 215.961856e6
+        traffic = 492.030720e6 + 217.395456e6
         traffic_source = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_tc_final_ncu_full_summary.txt)"
     roofline = {
         "bound": "hbm",
