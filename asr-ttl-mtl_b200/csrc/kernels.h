@@ -27,7 +27,7 @@ struct LogmelArgs {
                              // whether the dynamic-range clamp touches the utterance at all)
     uint32_t* tile_keys;     // device, [tiles of 128 frames][2] or nullptr: max key and ~min key of every tile (tcgen05)
     int global_max;
-    int fused_norm;          // the last CTA to finish an utterance normalises it in place
+    int fused_norm;          // the normalisation happens inside the front-end kernel (no pass 2)
     int n_rows;              // rows of the mel partial-sum tile (DeviceTables::n_rows)
     const DeviceTables* tables;  // device
 };
@@ -35,8 +35,9 @@ struct LogmelArgs {
 // FFT variant, one persistent launch: log10 mel + per-utterance max keys (+ in-place normalise when
 // a.fused_norm).  The counters in `a` must be zero when the kernel starts.
 cudaError_t launch_fft_fused(const LogmelArgs& a, int dtype, cudaStream_t stream);
-// tcgen05 variant: log10 mel + per-utterance max keys (the folded DFT as GEMMs on the tensor cores);
-// always followed by launch_normalise.  tables: device copy of the constant matrices.
+// tcgen05 variant (the folded DFT as GEMMs on the tensor cores), one persistent launch: with a.fused_norm the
+// finished [0, 1.x]-scaled log-mel, otherwise log10 mel + max keys for launch_normalise.  The counters and keys in `a`
+// must be zero when the kernel starts.  tables: device copy of the constant matrices.
 cudaError_t launch_tc_pass1(const LogmelArgs& a, const TcTables* tables, int dtype, cudaStream_t stream);
 // Pass 2 (shared by all variants): out = (max(out, g - 8) + 4) / 4.
 cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip,

@@ -1,15 +1,17 @@
 // tcgen05 (tensor-core) variant of the fused log-mel front-end for sm_100a: the folded DFT as four
 // 128 x 104 x 112 GEMMs per 128-frame tile, 3-product fp16 split precision (math: tc_core.cuh;
-// reference: whisper/audio.py:145-155).
+// reference: whisper/audio.py:145-156).  DESIGN.md section 4.1 has the picture; in short:
 //
-// One persistent CTA per SM, warp-specialised, no __syncthreads in the steady state (mbarriers only):
-//   4 + 4 fold warps: first stage the tile's 130 rows of 160 samples in shared memory at pitch 164 words with 16-byte
-//                     cp.async copies that complete on an mbarrier (next tile prefetched into L2; chunks that touch
-//                     a clip edge - reflect padding, zero tail, `lengths` - or are unaligned are written by hand);
-//                     then one thread per frame (= TMEM lane).  The E warps compute ee / eo, the O warps oe / oo
-//                     (window multiply and both folds fused: 5 flops per two values), split every value
-//                     into fp16 hi + lo and write the packed pairs straight into TENSOR MEMORY as the
-//                     A operand (tcgen05.st) - the data never touch shared memory again;
+// One persistent CTA per SM, 20 warps, warp-specialised, no __syncthreads in the steady state (mbarriers only):
+//   loader warp     : ONE TMA tensor copy per tile brings the 130 rows of 160 samples into shared memory at pitch 164
+//                     words (a 4-D tensor map whose rows overlap, see "loaders"); the next tile is prefetched into L2;
+//                     a clip's first / last tile: the copy zero-fills what it cannot address and the warp rewrites the
+//                     1-3 rows of real / reflected samples.  (`lengths` cuts, int16 PCM, unaligned rows: the fold warps
+//                     stage the tile themselves with cp.async / converted samples.)
+//   4 + 4 fold warps: one thread per frame (= TMEM lane), two warps per lane quadrant that split every sweep between
+//                     them.  E sweep: ee / eo, then O sweep: oe / oo (window multiply and both folds fused, packed
+//                     FMUL2 / FFMA2), every value split into fp16 hi + lo and written straight into TENSOR MEMORY as
+//                     the A operand (tcgen05.st) - the data never touch shared memory again;
 //   MMA warp        : one elected thread issues, per unit, 6 K-steps x 3 passes + 2 leftover steps of
 //                     tcgen05.mma.kind::f16 (M 128, N 104, K 16; A from TMEM, B = the constant matrix from
 //                     shared memory, fp32 accumulator in TMEM): hi Bh + lo Bh + hi Bl, then
@@ -17,13 +19,16 @@
 //   4 + 4 epilogue  : two warps per TMEM lane quadrant pull their half of the 104 accumulator columns
 //     warps           into registers at once (tcgen05.ld), release the accumulator, and add w d^2 to the mels
 //                     of each bin - mel structure and weights are compile-time constants (FFMA immediates),
-//                     partial sums in registers; after the 4th unit: log10(max(., 1e-10)), 128-byte
-//                     coalesced row stores and the utterance's max key (warp REDUX + one atomicMax).
-// Tensor memory is exactly full: 408 operand columns (4 units x [hi | lo], tc_core.cuh) + 104 accumulator.
-//   3 normaliser    : the epilogue warp that completes an utterance (per-clip counter) queues it; these warps apply
-//     warps           max(x, g - 8), (x + 4) / 4 in place while the utterance's 0.96 MB is still L2-resident, so the
+//                     partial sums in registers; after the 4th unit: log10(max(., 1e-10)), (x + 4) / 4, 128-byte
+//                     coalesced row stores, the utterance's and the tile's extremes (warp REDUX + atomicMax);
+//   2 normaliser    : once an utterance is complete (per-clip counter) decide from its and the tile's extremes what the
+//     warps           clamp at max - 8 does to each of this CTA's tiles: nothing (the usual case), a constant fill
+//                     (digital silence, zero padding) or a clamp in place while the tile is still in L2 - so the
 //                     front-end is one launch whose DRAM traffic is the algorithmic read + write.
-// (One max over the whole call, or very long utterances: the shared pass-2 kernel normalises instead.)
+// Tensor memory is exactly full: 408 operand columns (4 units x [hi | lo], tc_core.cuh) + 104 accumulator; so is shared
+// memory (DFT matrices + one audio tile).  The hot code of all roles has to fit the 32 KB instruction cache: loops over
+// table rows instead of unrolled code wherever the work is regular, and no bring-up code in the production build.
+// (One max over a whole multi-utterance call: the shared pass-2 kernel normalises instead.)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
