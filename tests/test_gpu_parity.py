@@ -279,6 +279,23 @@ def test_full_size_batch_properties(b200, n_mels):
     assert float(out.double().sum(dim=(1, 2)).sum()) == float(again.double().sum(dim=(1, 2)).sum())
 
 
+def test_large_batch_indexing(b200):
+    """BASELINE config 5 shape of work on one GPU: thousands of 30 s clips in one call (64-bit tile / row offsets, the
+    per-tile workspace, the tensor map's batch dimension) - every clip equals its own single-clip call, bit for bit."""
+    n_clips = 3001
+    gen = torch.Generator(device=DEV).manual_seed(99)
+    base = (0.1 * torch.randn(7, 480000, generator=gen, device=DEV)).clamp_(-1, 1)
+    audio = base.repeat(n_clips // 7 + 1, 1)[:n_clips].contiguous()
+    audio[1234, 200000:] = 0.0                       # one clip with a silent tail (clamp path inside a big batch)
+    out = b200.log_mel_spectrogram_batch(audio)
+    assert tuple(out.shape) == (n_clips, 80, 3000) and torch.isfinite(out).all()
+    for i in (0, 6, 7, 1234, 1500, n_clips - 1):
+        assert torch.equal(out[i], b200.log_mel_spectrogram_batch(audio[i:i + 1])[0]), i
+    assert torch.equal(out[7 * 11 + 3], out[3])      # replicas at different batch positions
+    del out, audio
+    torch.cuda.empty_cache()
+
+
 def test_long_single_utterance(b200):
     # one hour-scale file in one call (transcribe path): one max over the whole file
     x = signals.make_signal("gauss", 16000 * 600, 3)  # 10 minutes
