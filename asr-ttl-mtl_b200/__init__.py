@@ -13,6 +13,7 @@ from .audio import (  # noqa: F401
     N_SAMPLES_PER_TOKEN,
     SAMPLE_RATE,
     TOKENS_PER_SECOND,
+    collate_log_mels,
     gpu_launches,
     load_audio,
     log_mel_spectrogram,

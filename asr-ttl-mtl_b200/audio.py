@@ -288,6 +288,42 @@ def log_mel_spectrogram_batch(
     return _run(audio, n_mels, padding, lengths, 0, variant, out, allow_pcm16=True, l2_chunk_clips=l2_chunk_clips)
 
 
+def collate_log_mels(
+    waveforms,
+    n_mels: int = 80,
+    device: Optional[Union[str, torch.device]] = None,
+    *,
+    length: int = N_SAMPLES,
+    variant: str = "auto",
+) -> torch.Tensor:
+    """``batch['mels']`` for a list of un-padded waveforms, in one front-end call on the GPU.
+
+    What ``MultiTaskSpeechDataset.load_and_process_audio`` + ``collate_fn`` build one clip at a time on the CPU
+    (speech_disorder/dataset.py:82-89,179) — ``torch.stack([log_mel_spectrogram(pad_or_trim(w)) for w in waveforms])``,
+    shape ``[B, n_mels, length // 160]`` — built here from the raw clips: each is trimmed to ``length`` samples, only
+    its real samples cross PCIe, and the zero tail of ``pad_or_trim`` (audio.py:83-86) is never materialised: the
+    kernel gets the clip lengths and treats the rest of each row as zeros.  Float32 or int16 PCM clips (all the same kind).
+    A clip that cannot be processed raises — the reference's silent ``zeros((80, 3000))`` fallback is not reproduced.
+    """
+    _require_cuda()
+    if len(waveforms) == 0:
+        raise ValueError("collate_log_mels: empty batch")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda":
+        raise RuntimeError("collate_log_mels runs on a CUDA device (this front-end has no CPU fallback)")
+    clips = [w if torch.is_tensor(w) else torch.from_numpy(np.ascontiguousarray(w)) for w in waveforms]
+    dtype = clips[0].dtype
+    if dtype not in (torch.float32, torch.int16) or any(c.dtype != dtype or c.dim() != 1 for c in clips):
+        raise RuntimeError("collate_log_mels: expected 1-D float32 (or all int16 PCM) waveforms")
+    lens = torch.tensor([min(int(c.shape[0]), length) for c in clips], dtype=torch.int32)
+    staged = torch.empty((len(clips), length), dtype=dtype, device=dev)   # rows past `lens` stay unwritten and unread
+    for i, c in enumerate(clips):
+        n = int(lens[i])
+        if n > 0:
+            staged[i, :n].copy_(c[:n], non_blocking=True)
+    return log_mel_spectrogram_batch(staged, n_mels=n_mels, lengths=lens.to(dev, non_blocking=True), variant=variant)
+
+
 def gpu_launches() -> int:
     """Kernels launched by libb200mel.so in this process (bench.py's ``gpu_launches``)."""
     return _native.launch_count()

@@ -164,6 +164,24 @@ def test_dynamic_range_clamp_paths(b200):
     assert torch.equal(again[5:10], got) and torch.equal(again[10], got[2])
 
 
+def test_collate_log_mels_equals_the_dataset_path(b200):
+    """raw variable-length clips -> batch['mels'], equal to dataset.py:82-89 + collate (:179)."""
+    rng = np.random.default_rng(8)
+    lens = [16000, 123457, 480000, 480000 + 5000, 300]          # short, odd, exact, to be trimmed, very short
+    clips = [(0.1 * rng.standard_normal(n)).astype(np.float32) for n in lens]
+    got = b200.collate_log_mels(clips, device=DEV)
+    assert tuple(got.shape) == (len(clips), 80, 3000) and got.device.type == "cuda"
+    for i, c in enumerate(clips):
+        want = orc.logmel_f32_port(orc.pad_or_trim_oracle(c, 480000), 80)
+        assert _maxerr(got[i], want) <= TOL, (i, _maxerr(got[i], want))
+    pcm = [np.round(c * 32767).astype(np.int16) for c in clips]
+    got16 = b200.collate_log_mels(pcm, device=DEV)
+    ref16 = b200.collate_log_mels([p.astype(np.float32) / 32768.0 for p in pcm], device=DEV)
+    assert torch.equal(got16, ref16)
+    with pytest.raises(ValueError):
+        b200.collate_log_mels([], device=DEV)
+
+
 def test_pcm16_ingest_is_bit_equal_to_the_float_path(b200):
     q = np.stack([signals.make_pcm16(32000, 60 + i) for i in range(4)])
     f = q.astype(np.float32) / 32768.0  # audio.py:62
