@@ -21,6 +21,7 @@ DTYPE_F32, DTYPE_S16 = 0, 1
 VARIANT_AUTO, VARIANT_FFT, VARIANT_TCGEN05 = 0, 1, 2
 FLAG_GLOBAL_MAX = 1
 FLAG_TILE_KEYS = 2
+FLAG_OUT_F16 = 4
 ABI_VERSION = 1
 
 #: every symbol include/b200mel.h declares: (restype, argtypes)

@@ -166,7 +166,8 @@ def _frames_or_raise(n_samples: int, padding: int) -> int:
 
 
 def _run(audio: torch.Tensor, n_mels: int, padding: int, lengths, flags: int, variant: str,
-         out: Optional[torch.Tensor], allow_pcm16: bool, l2_chunk_clips: int = 0) -> torch.Tensor:
+         out: Optional[torch.Tensor], allow_pcm16: bool, l2_chunk_clips: int = 0,
+         out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """``audio`` 1-D/2-D on CPU or CUDA -> log-mel on the same device, squeezed like the input."""
     assert n_mels in {80, 128}, f"Unsupported n_mels: {n_mels}"
     dtype = _validate_waveform(audio, allow_pcm16)
@@ -188,15 +189,21 @@ def _run(audio: torch.Tensor, n_mels: int, padding: int, lengths, flags: int, va
         variant_id = VARIANTS[variant]
     except KeyError:
         raise ValueError(f"unknown variant {variant!r}; expected one of {sorted(VARIANTS)}") from None
+    if out_dtype not in (torch.float32, torch.float16):
+        raise ValueError(f"out_dtype must be torch.float32 or torch.float16, got {out_dtype}")
+    if out_dtype == torch.float16:
+        if (flags & _native.FLAG_GLOBAL_MAX) and batch > 1:
+            raise ValueError("float16 output needs one max per utterance (log_mel_spectrogram_batch) or a single utterance")
+        flags |= _native.FLAG_OUT_F16
 
     if wave.is_cuda:
         index = wave.device.index if wave.device.index is not None else torch.cuda.current_device()
         plan = _plan(index, n_mels)
         with torch.cuda.device(index):
             if out is None:
-                out = torch.empty(shape, dtype=torch.float32, device=wave.device)
-            elif out.shape != shape or out.dtype != torch.float32 or out.device != wave.device or not out.is_contiguous():
-                raise ValueError(f"out must be a contiguous float32 {shape} tensor on {wave.device}")
+                out = torch.empty(shape, dtype=out_dtype, device=wave.device)
+            elif out.shape != shape or out.dtype != out_dtype or out.device != wave.device or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous {out_dtype} {shape} tensor on {wave.device}")
             len_ptr = None
             if lengths is not None:
                 lengths = torch.as_tensor(lengths).to(device=wave.device, dtype=torch.int32).contiguous()
@@ -215,9 +222,9 @@ def _run(audio: torch.Tensor, n_mels: int, padding: int, lengths, flags: int, va
         index = torch.cuda.current_device()
         plan = _plan(index, n_mels)
         if out is None:
-            out = torch.empty(shape, dtype=torch.float32)
-        elif out.shape != shape or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
-            raise ValueError(f"out must be a contiguous float32 {shape} CPU tensor")
+            out = torch.empty(shape, dtype=out_dtype)
+        elif out.shape != shape or out.dtype != out_dtype or out.is_cuda or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous {out_dtype} {shape} CPU tensor")
         len_ptr = None
         if lengths is not None:
             lengths = torch.as_tensor(lengths).to(device="cpu", dtype=torch.int32).contiguous()
@@ -267,6 +274,7 @@ def log_mel_spectrogram_batch(
     out: Optional[torch.Tensor] = None,
     variant: str = "auto",
     l2_chunk_clips: int = 0,
+    out_dtype: torch.dtype = torch.float32,
 ):
     """Batched front-end with PER-UTTERANCE normalisation: ``[B, L] -> [B, n_mels, T]``.
 
@@ -277,7 +285,8 @@ def log_mel_spectrogram_batch(
     ``audio`` is float32 in [-1, 1] or int16 PCM (scaled by 1/32768 in-kernel, the
     arithmetic of audio.py:62).  ``lengths`` (optional, ``[B]``) gives the real samples of
     each row; the rest of the row counts as zeros without being read, i.e. the rows
-    behave as ``pad_or_trim``-med clips (audio.py:83-86).
+    behave as ``pad_or_trim``-med clips (audio.py:83-86).  ``out_dtype=torch.float16`` stores the float32 result
+    rounded to half (what the fp16 model gets after transcribe.py:286's ``.to(dtype)``), halving the bytes written.
     """
     if not torch.is_tensor(audio):
         audio = torch.from_numpy(audio)
@@ -285,7 +294,8 @@ def log_mel_spectrogram_batch(
         audio = audio.to(device)
     if audio.dim() != 2:
         raise RuntimeError(f"log_mel_spectrogram_batch: expected a 2D [B, L] waveform tensor, got {audio.dim()}D")
-    return _run(audio, n_mels, padding, lengths, 0, variant, out, allow_pcm16=True, l2_chunk_clips=l2_chunk_clips)
+    return _run(audio, n_mels, padding, lengths, 0, variant, out, allow_pcm16=True, l2_chunk_clips=l2_chunk_clips,
+                out_dtype=out_dtype)
 
 
 def collate_log_mels(

@@ -275,6 +275,7 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     a.n_frames = static_cast<int>(n_frames);
     a.n_mels = plan->n_mels;
     a.out = out;
+    a.out_f16 = (flags & B200MEL_FLAG_OUT_F16) ? 1 : 0;
     a.max_keys = keys;
     a.done_counters = keys + batch;
     a.tile_counter = keys + 2 * batch;
@@ -291,6 +292,7 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     a.fused_norm = ((!global_max || batch == 1) && (variant == B200MEL_VARIANT_TCGEN05 || tiles_per_clip <= kMaxFusedNormTiles)) ? 1 : 0;
     a.n_rows = plan->n_rows;
     a.tables = plan->d_tables;
+    if (a.out_f16 && !(variant == B200MEL_VARIANT_TCGEN05 && a.fused_norm)) return B200MEL_ERR_BAD_ARGUMENT;
     if (variant == B200MEL_VARIANT_TCGEN05)
         B200_CUDA(launch_tc_pass1(a, plan->d_tc_tables, dtype, stream));
     else
@@ -318,6 +320,7 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
     const size_t in_elem = dtype == B200MEL_F32 ? sizeof(float) : sizeof(int16_t);
     const int64_t elems_per_clip = static_cast<int64_t>(plan->n_mels) * n_frames;
     const bool global_max = (flags & B200MEL_FLAG_GLOBAL_MAX) != 0;
+    const size_t out_elem = (flags & B200MEL_FLAG_OUT_F16) ? 2 : 4;
     // chunk so that copy-in, compute and copy-out of neighbouring chunks overlap; a global max
     // needs every un-normalised value on the device at once, so it runs as a single chunk
     int64_t chunk = global_max ? batch : 16;
@@ -337,7 +340,7 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
         // the slot's previous chunk must have drained before its buffers are reused / regrown
         B200_CUDA(cudaStreamSynchronize(s.stream));
         B200_CUDA(ensure(&s.d_in, &s.in_bytes, static_cast<size_t>(n) * n_samples * in_elem + 16));
-        B200_CUDA(ensure(reinterpret_cast<void**>(&s.d_out), &s.out_bytes, static_cast<size_t>(n) * elems_per_clip * 4));
+        B200_CUDA(ensure(reinterpret_cast<void**>(&s.d_out), &s.out_bytes, static_cast<size_t>(n) * elems_per_clip * out_elem));
         B200_CUDA(ensure(&s.d_ws, &s.ws_bytes, b200mel_workspace_bytes_tiles(n, n_frames)));
         const char* src = static_cast<const char*>(audio_host) + static_cast<size_t>(c0) * stride_b * in_elem;
         if (stride_b == n_samples || n == 1) {
@@ -356,7 +359,8 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
         result = b200mel_logmel_device(plan, s.d_in, dtype, n, n_samples, n_samples, d_len, right_zero_pad, s.d_out,
                                        s.d_ws, flags | B200MEL_FLAG_TILE_KEYS, variant, 0, s.stream);
         if (result != B200MEL_OK) break;
-        B200_CUDA(cudaMemcpyAsync(out_host + c0 * elems_per_clip, s.d_out, static_cast<size_t>(n) * elems_per_clip * 4,
+        B200_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(out_host) + static_cast<size_t>(c0) * elems_per_clip * out_elem, s.d_out,
+                                  static_cast<size_t>(n) * elems_per_clip * out_elem,
                                   cudaMemcpyDeviceToHost, s.stream));
     }
     for (int i = 0; i < kHostSlots; ++i)

@@ -19,7 +19,8 @@ struct LogmelArgs {
     int64_t batch;           // utterances in this launch
     int n_frames;            // T = total / 160
     int n_mels;
-    float* out;              // device, [batch, n_mels, T]
+    float* out;              // device, [batch, n_mels, T] (IEEE half when out_f16, tcgen05 variant only)
+    int out_f16;
     uint32_t* max_keys;      // device, [batch] (or [1] with global_max), order-preserving keys
     uint32_t* done_counters; // device, [batch]: warps that finished a tile of the utterance (fused normalise)
     uint32_t* tile_counter;  // device, [1]: the persistent kernel's tile queue head

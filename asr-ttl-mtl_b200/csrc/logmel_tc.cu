@@ -230,51 +230,69 @@ __device__ __forceinline__ float4 normalise4(float4 x, float f) {
     return x;
 }
 
+// ---- output element type: float32 (the reference's dtype) or IEEE half (B200MEL_FLAG_OUT_F16) ----
+__device__ __forceinline__ void out_store(float* p, float v) { *p = v; }
+__device__ __forceinline__ void out_store(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ float out_load(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float out_load(const __half* p) { return __half2float(__ldcg(p)); }
+__device__ __forceinline__ float4 out_load4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 out_load4(const __half* p) {
+    const uint2 r = __ldcg(reinterpret_cast<const uint2*>(p));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void out_store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void out_store4(__half* p, float4 v) {
+    uint2 r;
+    r.x = tc_half2_bits(__floats2half2_rn(v.x, v.y));
+    r.y = tc_half2_bits(__floats2half2_rn(v.z, v.w));
+    *reinterpret_cast<uint2*>(p) = r;
+}
+
 // one warp overwrites one tile with the clamp value (every value of the tile was below it): stores only
-template <int NM>
-__device__ __forceinline__ void fill_tile_tc(float* __restrict__ tile_out, int64_t pitch, int frames, float v, int lane) {
-    if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & 15u) == 0 && (frames & 3) == 0) {
+template <int NM, typename OutT>
+__device__ __forceinline__ void fill_tile_tc(OutT* __restrict__ tile_out, int64_t pitch, int frames, float v, int lane) {
+    if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & (4 * sizeof(OutT) - 1)) == 0 && (frames & 3) == 0) {
         if (lane < (frames >> 2)) {
-            float* p = tile_out + 4 * lane;
+            OutT* p = tile_out + 4 * lane;
             const float4 v4 = make_float4(v, v, v, v);
 #pragma unroll 4
-            for (int row = 0; row < NM; ++row, p += pitch) *reinterpret_cast<float4*>(p) = v4;
+            for (int row = 0; row < NM; ++row, p += pitch) out_store4(p, v4);
         }
     } else {
-        for (int i = lane; i < NM * frames; i += 32) tile_out[(i / frames) * pitch + i % frames] = v;
+        for (int i = lane; i < NM * frames; i += 32) out_store(tile_out + (i / frames) * pitch + i % frames, v);
     }
 }
 
 // one warp clamps one tile (NM rows of `frames` values at `pitch`) in place
-template <int NM>
-__device__ __forceinline__ void normalise_tile_tc(float* __restrict__ tile_out, int64_t pitch, int frames, float g /* the clamp in rescaled units */, int lane) {
-    if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & 15u) == 0) {
-        // whole mel rows (lane = float4 column, 512 contiguous bytes), four rows in flight
+template <int NM, typename OutT>
+__device__ __forceinline__ void normalise_tile_tc(OutT* __restrict__ tile_out, int64_t pitch, int frames, float g /* the clamp in rescaled units */, int lane) {
+    if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & (4 * sizeof(OutT) - 1)) == 0) {
+        // whole mel rows (lane = 4-value column), four rows in flight
         if (lane < (frames >> 2)) {
-            float* p = tile_out + 4 * lane;
+            OutT* p = tile_out + 4 * lane;
             int row = 0;
 #pragma unroll 1
             for (; row + 3 < NM; row += 4, p += 4 * pitch) {
-                float4 x0 = __ldcg(reinterpret_cast<float4*>(p)), x1 = __ldcg(reinterpret_cast<float4*>(p + pitch));
-                float4 x2 = __ldcg(reinterpret_cast<float4*>(p + 2 * pitch)), x3 = __ldcg(reinterpret_cast<float4*>(p + 3 * pitch));
-                *reinterpret_cast<float4*>(p) = normalise4(x0, g);
-                *reinterpret_cast<float4*>(p + pitch) = normalise4(x1, g);
-                *reinterpret_cast<float4*>(p + 2 * pitch) = normalise4(x2, g);
-                *reinterpret_cast<float4*>(p + 3 * pitch) = normalise4(x3, g);
+                const float4 x0 = out_load4(p), x1 = out_load4(p + pitch), x2 = out_load4(p + 2 * pitch), x3 = out_load4(p + 3 * pitch);
+                out_store4(p, normalise4(x0, g));
+                out_store4(p + pitch, normalise4(x1, g));
+                out_store4(p + 2 * pitch, normalise4(x2, g));
+                out_store4(p + 3 * pitch, normalise4(x3, g));
             }
 #pragma unroll 1
-            for (; row < NM; ++row, p += pitch) *reinterpret_cast<float4*>(p) = normalise4(__ldcg(reinterpret_cast<float4*>(p)), g);
+            for (; row < NM; ++row, p += pitch) out_store4(p, normalise4(out_load4(p), g));
         }
         const int rest = frames & 3;                                           // 0 for whole clips (pitch % 4 == 0)
         if (rest != 0)
             for (int i = lane; i < NM * rest; i += 32) {
-                float* q = tile_out + (i / rest) * pitch + (frames & ~3) + i % rest;
-                *q = clamp_scaled(__ldcg(q), g);
+                OutT* q = tile_out + (i / rest) * pitch + (frames & ~3) + i % rest;
+                out_store(q, clamp_scaled(out_load(q), g));
             }
     } else {
         for (int i = lane; i < NM * frames; i += 32) {
-            float* q = tile_out + (i / frames) * pitch + i % frames;
-            *q = clamp_scaled(__ldcg(q), g);
+            OutT* q = tile_out + (i / frames) * pitch + i % frames;
+            out_store(q, clamp_scaled(out_load(q), g));
         }
     }
 }
@@ -511,7 +529,7 @@ struct TcNormState {
     uint32_t fenced_below[8];    // per epilogue warp: its rows of tiles with ordinal < this are visible gpu-wide
 };
 
-template <int NM, int HALF>
+template <int NM, int HALF, typename OutT>
 __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int debug_stage, long long* trace, const int trace_first, TcBarriers* bars,
                                               TcNormState* norm, float* s_straddle,
                                               uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
@@ -593,7 +611,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                 const bool live = t < a.n_frames;
                 constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
                 const int64_t pitch = a.n_frames;
-                float* const out = a.out + (prev.clip * NM + m_begin) * pitch + t;
+                OutT* const out = reinterpret_cast<OutT*>(a.out) + (prev.clip * NM + m_begin) * pitch + t;
                 // With the normalisation fused, the affine half of it, (x + 4) / 4, is applied here (one FFMA, the same
                 // single rounding as audio.py:156) and only the clamp at max - 8 is left for the normaliser warps - which
                 // skip the utterance when its smallest value is not below max - 8 (tracked here as well).
@@ -610,15 +628,15 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
                         const float2 l2 = make_float2(log2_clamped(acc[m - L::acc_base(HALF)]), log2_clamped(acc[m + 1 - L::acc_base(HALF)]));
                         const float2 lg = __fmul2_rn(l2, make_float2(kLog10Of2, kLog10Of2));
                         const float2 y = __ffma2_rn(lg, scale2, shift2);
-                        out[static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin)] = y.x;
-                        out[static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1 - m_begin)] = y.y;
+                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin), y.x);
+                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1 - m_begin), y.y);
                         mx = max_nan(mx, max_nan(lg.x, lg.y));
                         mn = fminf(mn, fminf(lg.x, lg.y));
                     }
                     if constexpr ((m_end - m_begin) % 2 == 1) {
                         constexpr int m = m_end - 1;
                         const float lg = log10_clamped(acc[m - L::acc_base(HALF)]);
-                        out[static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin)] = fmaf(lg, scale, shift);
+                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin), fmaf(lg, scale, shift));
                         mx = max_nan(mx, lg);
                         mn = fminf(mn, lg);
                     }
@@ -662,7 +680,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, const int deb
 
 // BRINGUP = false is the production build: the timeline stamps and the staged bring-up modes (B200MEL_TC_TRACE,
 // B200MEL_TC_DEBUG) fold away, which also keeps the hot code inside the 32 KB instruction cache.
-template <typename InT, int NM, bool BRINGUP>
+template <typename InT, int NM, bool BRINGUP, typename OutT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ CUtensorMap audio_map, const int tma_rows,
                  const unsigned char* __restrict__ operands, const int debug_arg, long long* __restrict__ trace_arg, const int trace_first) {
@@ -779,8 +797,8 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         // ===== epilogue warps =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         if (debug_stage > 0 && debug_stage < 4) total_tiles = 0;
-        if (warp < kWarpEpi1) epilogue_role<NM, 0>(a, debug_stage, trace, trace_first, &bars, &norm_state, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
-        else epilogue_role<NM, 1>(a, debug_stage, trace, trace_first, &bars, &norm_state, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        if (warp < kWarpEpi1) epilogue_role<NM, 0, OutT>(a, debug_stage, trace, trace_first, &bars, &norm_state, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        else epilogue_role<NM, 1, OutT>(a, debug_stage, trace, trace_first, &bars, &norm_state, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == kWarpMma && (debug_stage == 0 || debug_stage >= 3)) {
@@ -924,9 +942,9 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                     const bool fill = __shfl_sync(0xffffffffu, action, src) == 2;
                     const int frames = a.n_frames - t0 < kTcTileFrames ? a.n_frames - t0 : kTcTileFrames;
                     const float floor_y = ((gs - 8.0f) + 4.0f) * 0.25f;
-                    float* tile_out = a.out + clip * NM * static_cast<int64_t>(a.n_frames) + t0;
-                    if (fill) fill_tile_tc<NM>(tile_out, a.n_frames, frames, floor_y, lane);
-                    else normalise_tile_tc<NM>(tile_out, a.n_frames, frames, floor_y, lane);
+                    OutT* tile_out = reinterpret_cast<OutT*>(a.out) + clip * NM * static_cast<int64_t>(a.n_frames) + t0;
+                    if (fill) fill_tile_tc<NM, OutT>(tile_out, a.n_frames, frames, floor_y, lane);
+                    else normalise_tile_tc<NM, OutT>(tile_out, a.n_frames, frames, floor_y, lane);
                 }
             }
         }
@@ -957,9 +975,11 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     if (err != cudaSuccess) return err;
     if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
     if (sms_by_device[device] == 0) {
-        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (err != cudaSuccess) return err;
-        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, false, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (err != cudaSuccess) return err;
         int sms = 0;
         if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return err;
@@ -1022,11 +1042,13 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     constexpr size_t kTraceBytes = sizeof(long long) * (kTraceWords + 6 * kStampCtas + TC_TILE_STAMPS);
     if (want_trace && trace == nullptr) { cudaMalloc(&trace, kTraceBytes); }
     if (want_trace) cudaMemsetAsync(trace, 0, kTraceBytes, stream);
-    if (want_trace || debug_stage != 0)
-        logmel_tc_kernel<InT, NM, true><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, debug_stage,
-                                                                                    want_trace ? trace : nullptr, trace_first);
+    if (a.out_f16)
+        logmel_tc_kernel<InT, NM, false, __half><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, 0, nullptr, 0);
+    else if (want_trace || debug_stage != 0)
+        logmel_tc_kernel<InT, NM, true, float><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, debug_stage,
+                                                                                           want_trace ? trace : nullptr, trace_first);
     else
-        logmel_tc_kernel<InT, NM, false><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, 0, nullptr, 0);
+        logmel_tc_kernel<InT, NM, false, float><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, 0, nullptr, 0);
     count_launch();
     err = cudaGetLastError();
     if (want_trace && err == cudaSuccess) {   // bring-up only: synchronises and prints CTA 0's timeline

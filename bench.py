@@ -49,9 +49,9 @@ THROTTLE_BITS = {
 }
 
 
-def bytes_per_clip(n_mels: int, in_bytes: int = 4) -> int:
+def bytes_per_clip(n_mels: int, in_bytes: int = 4, out_bytes: int = 4) -> int:
     """Algorithmic HBM bytes per 30 s clip: waveform read once + log-mel written once."""
-    return N_SAMPLES * in_bytes + n_mels * N_FRAMES * 4
+    return N_SAMPLES * in_bytes + n_mels * N_FRAMES * out_bytes
 
 
 def load_peaks() -> tuple[float, str]:
@@ -259,10 +259,11 @@ def run_own_arm(args) -> None:
         (0.1 * torch.randn(B, N_SAMPLES, generator=gen, device=device, dtype=torch.float32)).clamp_(-1.0, 1.0)
         for _ in range(2)
     ]
-    out = torch.empty(B, n_mels, N_FRAMES, device=device, dtype=torch.float32)
+    out_dtype = torch.float16 if args.out_dtype == "f16" else torch.float32
+    out = torch.empty(B, n_mels, N_FRAMES, device=device, dtype=out_dtype)
 
     def step(i: int) -> None:
-        b200.log_mel_spectrogram_batch(inputs[i & 1], n_mels=n_mels, out=out, variant=args.variant,
+        b200.log_mel_spectrogram_batch(inputs[i & 1], n_mels=n_mels, out=out, variant=args.variant, out_dtype=out_dtype,
                                        l2_chunk_clips=args.l2_chunk_clips)
 
     for i in range(max(args.warmup, 3)):
@@ -299,11 +300,11 @@ def run_own_arm(args) -> None:
     fused_kind = "tcgen05_pass" if prof["tcgen05_pass"][1] else "fft_pass"
     fused_ms, fused_launches = prof[fused_kind]
     norm_ms, norm_launches = prof["normalise"]
-    algo_bytes_step = B * bytes_per_clip(n_mels)
+    algo_bytes_step = B * bytes_per_clip(n_mels, out_bytes=2 if args.out_dtype == "f16" else 4)
     achieved = algo_bytes_step * args.steps / (fused_ms / 1e3) / 1e9 if fused_ms > 0 else None
     # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
     traffic, traffic_source = args.traffic_bytes, "--traffic-bytes" if args.traffic_bytes else None
-    if traffic is None and fused_kind == "tcgen05_pass" and n_mels == 80 and B == DEFAULT_BATCH:
+    if traffic is None and fused_kind == "tcgen05_pass" and n_mels == 80 and B == DEFAULT_BATCH and args.out_dtype == "f32":
         traffic = 492.030720e6 + 217.395456e6
         traffic_source = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_tc_final_ncu_full_summary.txt)"
     roofline = {
@@ -329,15 +330,15 @@ def run_own_arm(args) -> None:
     e2e_batch = args.e2e_batch
     host_in = torch.empty(e2e_batch, N_SAMPLES, dtype=torch.float32).pin_memory()
     host_in.copy_(inputs[0][:e2e_batch])
-    host_out = torch.empty(e2e_batch, n_mels, N_FRAMES, dtype=torch.float32).pin_memory()
+    host_out = torch.empty(e2e_batch, n_mels, N_FRAMES, dtype=out_dtype).pin_memory()
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
     for _ in range(2):
-        b200.log_mel_spectrogram_batch(host_in, n_mels=n_mels, out=host_out, variant=args.variant)
+        b200.log_mel_spectrogram_batch(host_in, n_mels=n_mels, out=host_out, variant=args.variant, out_dtype=out_dtype)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        b200.log_mel_spectrogram_batch(host_in, n_mels=n_mels, out=host_out, variant=args.variant)
+        b200.log_mel_spectrogram_batch(host_in, n_mels=n_mels, out=host_out, variant=args.variant, out_dtype=out_dtype)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_clips = sum_over_ranks(float(e2e_batch * e2e_steps))
@@ -345,7 +346,7 @@ def run_own_arm(args) -> None:
         "value": e2e_clips * CLIP_SECONDS / 3600.0 / e2e_s,
         "unit": "audio-hours/s",
         "h2d_bytes_per_step": e2e_batch * N_SAMPLES * 4,
-        "d2h_bytes_per_step": e2e_batch * n_mels * N_FRAMES * 4,
+        "d2h_bytes_per_step": e2e_batch * n_mels * N_FRAMES * (2 if args.out_dtype == "f16" else 4),
         "clips_per_step_per_gpu": e2e_batch,
         "steps": e2e_steps,
         "api": "log_mel_spectrogram_batch(pinned CPU tensor) -> b200mel_logmel_host",
@@ -356,12 +357,12 @@ def run_own_arm(args) -> None:
     # half the host-to-device bytes, bit-equal output.  Reported beside the fp32 number, not instead of it.
     host_pcm = (host_in * 32768.0).round().clamp_(-32768, 32767).to(torch.int16).pin_memory()
     for _ in range(2):
-        b200.log_mel_spectrogram_batch(host_pcm, n_mels=n_mels, out=host_out, variant=args.variant)
+        b200.log_mel_spectrogram_batch(host_pcm, n_mels=n_mels, out=host_out, variant=args.variant, out_dtype=out_dtype)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        b200.log_mel_spectrogram_batch(host_pcm, n_mels=n_mels, out=host_out, variant=args.variant)
+        b200.log_mel_spectrogram_batch(host_pcm, n_mels=n_mels, out=host_out, variant=args.variant, out_dtype=out_dtype)
     torch.cuda.synchronize()
     pcm_s = max_over_ranks(time.perf_counter() - t0)
     e2e["pcm16_input"] = {"value": e2e_clips * CLIP_SECONDS / 3600.0 / pcm_s, "unit": "audio-hours/s",
@@ -405,6 +406,8 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=DEFAULT_BATCH, help="clips per step per GPU")
     ap.add_argument("--variant", default="auto", choices=["auto", "fft", "tcgen05"])
     ap.add_argument("--l2-chunk-clips", type=int, default=0)
+    ap.add_argument("--out-dtype", default="f32", choices=["f32", "f16"],
+                    help="f16: the float32 result rounded to half (SURVEY 8 f3, what transcribe feeds the fp16 model)")
     ap.add_argument("--e2e-batch", type=int, default=DEFAULT_BATCH)
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -67,6 +67,11 @@ typedef enum b200mel_variant {
                                       max - 8 (audio.py:155) re-touches only the tiles it changes: silent (zero-padded)
                                       tiles are filled, tiles wholly above the clamp are left alone.           */
 
+#define B200MEL_FLAG_OUT_F16 4u    /* `out` holds IEEE half instead of float32: the values of the float32 result rounded
+                                      to nearest (what transcribe.py:286 / decoding.py feed the fp16 model after their
+                                      .to(dtype)); half the write bytes.  tcgen05 variant, one max per utterance (or a
+                                      single utterance) only - otherwise B200MEL_ERR_BAD_ARGUMENT.                */
+
 typedef struct b200mel_plan b200mel_plan; /* opaque: filterbank bands + FFT tables on one device */
 
 int b200mel_abi_version(void);
@@ -96,7 +101,8 @@ size_t b200mel_workspace_bytes_tiles(int64_t batch, int64_t n_frames);
  *   lengths    device int32 [batch] or NULL: samples of each row that are real; the rest of the
  *              row is treated as zeros WITHOUT being read (pad_or_trim semantics, audio.py:83-86)
  *   right_zero_pad  the `padding` argument (audio.py:145-146); <= 0 is ignored
- *   out        device float32 [batch, n_mels, T] contiguous, T from b200mel_frames
+ *   out        device float32 [batch, n_mels, T] contiguous, T from b200mel_frames (IEEE half with
+ *              B200MEL_FLAG_OUT_F16; the pointer is passed through the same parameter)
  *   workspace  device scratch of b200mel_workspace_bytes(batch), or of b200mel_workspace_bytes_tiles(batch, T)
  *              together with B200MEL_FLAG_TILE_KEYS
  *   l2_chunk_clips  reserved (0): the persistent kernel walks the batch utterance-major, so an

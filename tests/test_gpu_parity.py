@@ -182,6 +182,32 @@ def test_collate_log_mels_equals_the_dataset_path(b200):
         b200.collate_log_mels([], device=DEV)
 
 
+def test_float16_emission_is_the_rounded_float32_result(b200, default_variant):
+    """out_dtype=float16 stores exactly what `.to(torch.float16)` of the float32 result gives
+    (transcribe.py:286 feeds the fp16 model that way), clamp paths included; float32 stays the default."""
+    rng = np.random.default_rng(21)
+    n = 16000 * 9
+    clips = (0.1 * rng.standard_normal((4, n))).astype(np.float32)
+    clips[1, n // 2:] = 0.0                    # silent tail: tiles filled by the clamp path
+    clips[2, 30000:60000] *= 1e-5              # value-by-value clamp
+    x = torch.from_numpy(clips).to(DEV)
+    if default_variant == "fft":
+        with pytest.raises(Exception):
+            b200.log_mel_spectrogram_batch(x, out_dtype=torch.float16)
+        return
+    f32 = b200.log_mel_spectrogram_batch(x)
+    f16 = b200.log_mel_spectrogram_batch(x, out_dtype=torch.float16)
+    assert f16.dtype == torch.float16 and f16.shape == f32.shape and f16.is_contiguous()
+    assert torch.equal(f16, f32.half())
+    for n_mels in (80, 128):                   # transcribe's call shape: one utterance, 30 s of right padding
+        one32 = b200.log_mel_spectrogram_batch(x[:1], n_mels=n_mels, padding=480000)
+        one16 = b200.log_mel_spectrogram_batch(x[:1], n_mels=n_mels, padding=480000, out_dtype=torch.float16)
+        assert torch.equal(one16, one32.half())
+    host16 = b200.log_mel_spectrogram_batch(torch.from_numpy(clips), out_dtype=torch.float16)   # host buffers in and out
+    assert host16.device.type == "cpu" and torch.equal(host16, f16.cpu())
+    assert _maxerr(f16.float(), orc.logmel_f32_port_per_utterance(torch.from_numpy(clips), 80)) <= 1e-3   # half: 2^-11 relative
+
+
 def test_pcm16_ingest_is_bit_equal_to_the_float_path(b200):
     q = np.stack([signals.make_pcm16(32000, 60 + i) for i in range(4)])
     f = q.astype(np.float32) / 32768.0  # audio.py:62
