@@ -458,6 +458,42 @@ __device__ __forceinline__ void produce_tile(const LogmelArgs& a, const TileCoor
         if ((pt & 31) == 0) mbar_arrive(full);
         return;
     }
+    if constexpr (sizeof(InT) == 2) {
+        // int16 PCM, tile wholly inside the utterance, 16-byte aligned: every thread pulls its ~10 chunks of 8 samples
+        // (one 128-bit load each, all in flight at once), then scales them by 2^-15 into the fp32 rows (audio.py:62)
+        if (s0 >= 0 && s0 + kTcAudioSamples <= valid && ((reinterpret_cast<uintptr_t>(row) + 2u * static_cast<uint64_t>(s0)) & 15u) == 0) {
+            constexpr int kPcmChunks = kTcAudioSamples / 8;                      // 2590 chunks of 8 samples, 20 per row
+            constexpr int kPerThread = (kPcmChunks + kProducerThreads - 1) / kProducerThreads;
+            static_assert(kTcAudioSamples % 8 == 0 && kHop % 8 == 0, "the tile is a whole number of 8-sample chunks");
+            const uint4* src = reinterpret_cast<const uint4*>(row + s0);
+            uint4 raw[kPerThread];
+#pragma unroll
+            for (int i = 0; i < kPerThread; ++i) {
+                const int c = pt + i * kProducerThreads;
+                raw[i] = c < kPcmChunks ? __ldcg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int i = 0; i < kPerThread; ++i) {
+                const int c = pt + i * kProducerThreads;
+                if (c < kPcmChunks) {
+                    const int rr = c / (kHop / 8), col = (c - rr * (kHop / 8)) * 8;
+                    const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[2 * j] = static_cast<float>(static_cast<int16_t>(w[j] & 0xffffu)) * (1.0f / 32768.0f);
+                        v[2 * j + 1] = static_cast<float>(static_cast<int16_t>(w[j] >> 16)) * (1.0f / 32768.0f);
+                    }
+                    float4* dst = reinterpret_cast<float4*>(s_audio + rr * kTcRowPitch + col);
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+            __syncwarp();
+            if ((pt & 31) == 0) mbar_arrive(full);
+            return;
+        }
+    }
     // chunk c = 40 r + k covers samples s0 + 4c .. + 3 and lands at word 164 r + 4 k
     int r = pt / kChunksPerRow, k = pt - r * kChunksPerRow;
     for (int c = pt; c < kTileChunks; c += kProducerThreads) {
