@@ -101,9 +101,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // ---- tensor memory stores / loads (32 lanes x 32 bit per column, this warp's lane quadrant) ----
 // The stores carry no "memory" clobber: they alias nothing the compiler can see, and their ordering against the
 // tensor cores comes from tcgen05.wait::st + the fences, so shared-memory loads may be scheduled across them.
-__device__ __forceinline__ void tmem_st1(uint32_t t, uint32_t a) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(t), "r"(a));
-}
 __device__ __forceinline__ void tmem_st2(uint32_t t, uint32_t a, uint32_t b) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t), "r"(a), "r"(b));
 }

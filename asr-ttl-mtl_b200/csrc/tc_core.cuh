@@ -142,6 +142,9 @@ B200_HD void tc_split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
 }
 
 // ---- one sweep chunk: 8 slots of both units of a sweep, table driven -----------------------------------
+// (Three forms of the same chunk live in this header: this first table-driven one and the compile-time one below are
+// kept as independent statements of the math - the CPU emulator runs all three and requires bit-equal results - while
+// the kernel runs the third, tc_sweep_chunk_row.)
 // SWEEP 0 (E): slot r = 8 J + i is n = r;        sa = x[n] + x[400-n], sb = x[200-n] + x[200+n]
 //              unit 0 gets ee = w[n] sa + w[200-n] sb, unit 1 gets eo = w[n] sa - w[200-n] sb.
 // SWEEP 1 (O): slot r = 8 J + i is n = 100 - r;  sa = x[n] - x[400-n], sb = x[200-n] - x[200+n]
