@@ -12,7 +12,7 @@ import threading
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libb200mel.so")
+LIB_PATH = os.environ.get("B200MEL_LIB") or os.path.join(HERE, "lib", "libb200mel.so")   # (B200MEL_LIB: bring-up builds)
 
 # enums of include/b200mel.h
 OK = 0
@@ -22,7 +22,7 @@ VARIANT_AUTO, VARIANT_FFT, VARIANT_TCGEN05 = 0, 1, 2
 FLAG_GLOBAL_MAX = 1
 FLAG_TILE_KEYS = 2
 FLAG_OUT_F16 = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 #: every symbol include/b200mel.h declares: (restype, argtypes)
 SYMBOLS = {
@@ -36,11 +36,12 @@ SYMBOLS = {
     "b200mel_workspace_bytes": (c_size_t, [c_int64]),
     "b200mel_workspace_bytes_tiles": (c_size_t, [c_int64, c_int64]),
     "b200mel_logmel_device": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
-                                      c_void_p, c_void_p, c_uint, c_int, c_int, c_void_p]),
+                                      c_void_p, c_void_p, c_uint, c_int, c_void_p]),
     "b200mel_normalise_device": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_uint, c_void_p]),
     "b200mel_logmel_host": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                     c_void_p, c_uint, c_int]),
     "b200mel_launch_count": (c_uint64, []),
+    "b200mel_kernel_fault": (c_uint, [POINTER(c_uint)]),
     "b200mel_profile_enable": (c_int, [c_int]),
     "b200mel_profile_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_uint64)]),
 }
@@ -109,6 +110,13 @@ def frames(n_samples: int, padding: int = 0) -> int:
 
 def launch_count() -> int:
     return int(load().b200mel_launch_count())
+
+
+def kernel_fault() -> tuple[int, int]:
+    """(code, CTA) of a timed-out hand-over inside the tcgen05 kernel, (0, 0) if there never was one; synchronises."""
+    cta = c_uint(0)
+    code = int(load().b200mel_kernel_fault(ctypes.byref(cta)))
+    return code, int(cta.value)
 
 
 PROFILE_KINDS = ("fft_pass", "normalise", "tcgen05_pass", "other")

@@ -166,7 +166,7 @@ def _frames_or_raise(n_samples: int, padding: int) -> int:
 
 
 def _run(audio: torch.Tensor, n_mels: int, padding: int, lengths, flags: int, variant: str,
-         out: Optional[torch.Tensor], allow_pcm16: bool, l2_chunk_clips: int = 0,
+         out: Optional[torch.Tensor], allow_pcm16: bool,
          out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """``audio`` 1-D/2-D on CPU or CUDA -> log-mel on the same device, squeezed like the input."""
     assert n_mels in {80, 128}, f"Unsupported n_mels: {n_mels}"
@@ -192,8 +192,6 @@ def _run(audio: torch.Tensor, n_mels: int, padding: int, lengths, flags: int, va
     if out_dtype not in (torch.float32, torch.float16):
         raise ValueError(f"out_dtype must be torch.float32 or torch.float16, got {out_dtype}")
     if out_dtype == torch.float16:
-        if (flags & _native.FLAG_GLOBAL_MAX) and batch > 1:
-            raise ValueError("float16 output needs one max per utterance (log_mel_spectrogram_batch) or a single utterance")
         flags |= _native.FLAG_OUT_F16
 
     if wave.is_cuda:
@@ -214,7 +212,7 @@ def _run(audio: torch.Tensor, n_mels: int, padding: int, lengths, flags: int, va
             stream = torch.cuda.current_stream(wave.device)
             _native.check(lib.b200mel_logmel_device(
                 plan, wave.data_ptr(), dtype, batch, n_samples, stride_b, len_ptr, padding, out.data_ptr(),
-                workspace.data_ptr(), flags | _native.FLAG_TILE_KEYS, variant_id, int(l2_chunk_clips), stream.cuda_stream))
+                workspace.data_ptr(), flags | _native.FLAG_TILE_KEYS, variant_id, stream.cuda_stream))
             # the caching allocator may hand these blocks to another stream once we return
             workspace.record_stream(stream)
             wave.record_stream(stream)
@@ -273,7 +271,6 @@ def log_mel_spectrogram_batch(
     lengths=None,
     out: Optional[torch.Tensor] = None,
     variant: str = "auto",
-    l2_chunk_clips: int = 0,
     out_dtype: torch.dtype = torch.float32,
 ):
     """Batched front-end with PER-UTTERANCE normalisation: ``[B, L] -> [B, n_mels, T]``.
@@ -282,7 +279,7 @@ def log_mel_spectrogram_batch(
     ``MultiTaskSpeechDataset`` + ``collate_fn`` build one clip at a time
     (speech_disorder/dataset.py:82-89,179) — in a single launch sequence.
 
-    ``audio`` is float32 in [-1, 1] or int16 PCM (scaled by 1/32768 in-kernel, the
+    ``audio`` is float32 (any finite range) or int16 PCM (scaled by 1/32768 in-kernel, the
     arithmetic of audio.py:62).  ``lengths`` (optional, ``[B]``) gives the real samples of
     each row; the rest of the row counts as zeros without being read, i.e. the rows
     behave as ``pad_or_trim``-med clips (audio.py:83-86).  ``out_dtype=torch.float16`` stores the float32 result
@@ -294,8 +291,7 @@ def log_mel_spectrogram_batch(
         audio = audio.to(device)
     if audio.dim() != 2:
         raise RuntimeError(f"log_mel_spectrogram_batch: expected a 2D [B, L] waveform tensor, got {audio.dim()}D")
-    return _run(audio, n_mels, padding, lengths, 0, variant, out, allow_pcm16=True, l2_chunk_clips=l2_chunk_clips,
-                out_dtype=out_dtype)
+    return _run(audio, n_mels, padding, lengths, 0, variant, out, allow_pcm16=True, out_dtype=out_dtype)
 
 
 def collate_log_mels(

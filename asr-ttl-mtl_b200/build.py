@@ -44,13 +44,22 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds lib/libb200mel_trace.so instead: the same library with the tcgen05 kernel's timeline stamps
+    compiled in (-DB200MEL_TC_TRACE; tools/tc_trace.py loads it through B200MEL_LIB)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    if trace:
+        _build(os.path.join(LIBDIR, "libb200mel_switches.so"), srcs, force, verbose, ["-DB200MEL_TC_SWITCHES"])
+        return _build(os.path.join(LIBDIR, "libb200mel_trace.so"), srcs, force, verbose, ["-DB200MEL_TC_TRACE"])
+    return _build(LIB, srcs, force, verbose, [])
+
+
+def _build(LIB: str, srcs: list[str], force: bool, verbose: bool, extra: list[str]) -> str:
     deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     if not force and not _stale(LIB, deps):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB, *srcs]
@@ -63,4 +72,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv))

@@ -125,6 +125,8 @@ const char* b200mel_last_cuda_error(void) { return tl_cuda_error; }
 
 uint64_t b200mel_launch_count(void) { return launches_so_far(); }
 
+unsigned b200mel_kernel_fault(unsigned* cta) { return tc_kernel_fault(cta); }
+
 int b200mel_profile_enable(int on) {
     g_profile_on.store(on ? 1 : 0, std::memory_order_relaxed);
     return B200MEL_OK;
@@ -239,10 +241,10 @@ int b200mel_normalise_device(float* out, const void* workspace, int64_t batch, i
 int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype, int64_t batch,
                           int64_t n_samples, int64_t stride_b, const int32_t* lengths,
                           int64_t right_zero_pad, float* out, void* workspace, unsigned flags,
-                          int variant, int l2_chunk_clips, void* stream_v) {
+                          int variant, void* stream_v) {
     if (plan == nullptr || out == nullptr || workspace == nullptr) return B200MEL_ERR_NULL_POINTER;
     if (dtype != B200MEL_F32 && dtype != B200MEL_S16) return B200MEL_ERR_BAD_ARGUMENT;
-    if (batch < 0 || n_samples < 0 || stride_b < 0 || l2_chunk_clips < 0) return B200MEL_ERR_BAD_ARGUMENT;
+    if (batch < 0 || n_samples < 0 || stride_b < 0) return B200MEL_ERR_BAD_ARGUMENT;
     // the variant ncu picked: the tcgen05 kernel, unless this plan's filterbank could not be turned into its
     // compile-time band tables - then the shared-memory FFT kernel, which takes any banded filterbank
     if (variant == B200MEL_VARIANT_AUTO) variant = plan->d_tc_tables != nullptr ? B200MEL_VARIANT_TCGEN05 : B200MEL_VARIANT_FFT;
@@ -263,7 +265,6 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
 
     const int64_t elems_per_clip = static_cast<int64_t>(plan->n_mels) * n_frames;
     const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
-    (void)l2_chunk_clips;  // the persistent kernel walks the batch clip-major; nothing to chunk
 
     LogmelArgs a;
     a.audio = audio;
@@ -287,17 +288,21 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     }
     a.global_max = global_max;
     // one max per utterance (or a single utterance, where the call's max is the utterance's): normalised inside the
-    // front-end kernel.  The FFT variant's last CTA normalises the whole utterance, so very long ones go to pass 2;
-    // the tcgen05 variant normalises tile by tile and has no such limit.
-    a.fused_norm = ((!global_max || batch == 1) && (variant == B200MEL_VARIANT_TCGEN05 || tiles_per_clip <= kMaxFusedNormTiles)) ? 1 : 0;
+    // front-end kernel by the CTA that finishes the utterance - unless the utterance is so long that this would be a
+    // serial tail (whole-file transcription): then pass 2 normalises at full bandwidth.
+    const bool short_enough = variant == B200MEL_VARIANT_TCGEN05 ? tc_tiles_per_clip(n_frames) <= kTcMaxFusedNormTiles : tiles_per_clip <= kMaxFusedNormTiles;
+    a.fused_norm = ((!global_max || batch == 1) && short_enough) ? 1 : 0;
     a.n_rows = plan->n_rows;
     a.tables = plan->d_tables;
-    if (a.out_f16 && !(variant == B200MEL_VARIANT_TCGEN05 && a.fused_norm)) return B200MEL_ERR_BAD_ARGUMENT;
+    if (a.out_f16 && variant != B200MEL_VARIANT_TCGEN05) return B200MEL_ERR_BAD_ARGUMENT;
     if (variant == B200MEL_VARIANT_TCGEN05)
         B200_CUDA(launch_tc_pass1(a, plan->d_tc_tables, dtype, stream));
     else
         B200_CUDA(launch_fft_fused(a, dtype, stream));
-    if (!a.fused_norm) B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, global_max, stream));
+    if (!a.fused_norm) {
+        if (variant == B200MEL_VARIANT_TCGEN05) B200_CUDA(launch_tc_clamp(out, a.out_f16, keys, batch, elems_per_clip, global_max, stream));
+        else B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, global_max, stream));
+    }
     return B200MEL_OK;
 }
 
@@ -357,7 +362,7 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
             d_len = s.d_len;
         }
         result = b200mel_logmel_device(plan, s.d_in, dtype, n, n_samples, n_samples, d_len, right_zero_pad, s.d_out,
-                                       s.d_ws, flags | B200MEL_FLAG_TILE_KEYS, variant, 0, s.stream);
+                                       s.d_ws, flags | B200MEL_FLAG_TILE_KEYS, variant, s.stream);
         if (result != B200MEL_OK) break;
         B200_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(out_host) + static_cast<size_t>(c0) * elems_per_clip * out_elem, s.d_out,
                                   static_cast<size_t>(n) * elems_per_clip * out_elem,

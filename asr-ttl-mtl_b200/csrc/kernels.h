@@ -22,7 +22,8 @@ struct LogmelArgs {
     float* out;              // device, [batch, n_mels, T] (IEEE half when out_f16, tcgen05 variant only)
     int out_f16;
     uint32_t* max_keys;      // device, [batch] (or [1] with global_max), order-preserving keys
-    uint32_t* done_counters; // device, [batch]: warps that finished a tile of the utterance (fused normalise)
+    uint32_t* done_counters; // device, [batch]: epilogue warps that have finished a tile of the utterance (fused normalise:
+                             // whoever brings the count to 8 x tiles normalises the utterance)
     uint32_t* tile_counter;  // device, [1]: the persistent kernel's tile queue head
     uint32_t* min_keys;      // device, [batch]: ~key of the utterance's smallest log10 value (tcgen05 variant: decides
                              // whether the dynamic-range clamp touches the utterance at all)
@@ -37,9 +38,19 @@ struct LogmelArgs {
 // a.fused_norm).  The counters in `a` must be zero when the kernel starts.
 cudaError_t launch_fft_fused(const LogmelArgs& a, int dtype, cudaStream_t stream);
 // tcgen05 variant (the folded DFT as GEMMs on the tensor cores), one persistent launch: with a.fused_norm the
-// finished [0, 1.x]-scaled log-mel, otherwise log10 mel + max keys for launch_normalise.  The counters and keys in `a`
+// finished log-mel, otherwise (log10 mel + 4) / 4 and the max keys for launch_tc_clamp.  The counters and keys in `a`
 // must be zero when the kernel starts.  tables: device copy of the constant matrices.
 cudaError_t launch_tc_pass1(const LogmelArgs& a, const TcTables* tables, int dtype, cudaStream_t stream);
+// Clamp pass for the calls the tcgen05 kernel does not normalise itself: out = max(out, ((g - 8) + 4) / 4) on its already
+// rescaled values (float32 or half).
+cudaError_t launch_tc_clamp(void* out, int out_f16, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip, int global_max,
+                            cudaStream_t stream);
+// Code (0 = none) and CTA of a hand-over inside the tcgen05 kernel that timed out (a protocol bug: the kernel then ran to
+// its end with garbage in that launch's output instead of hanging); synchronises the device.
+unsigned tc_kernel_fault(unsigned* cta);
+// an utterance of more tiles than this is normalised by the pass-2 kernel (the in-kernel normaliser takes an utterance
+// with two warps)
+constexpr int64_t kTcMaxFusedNormTiles = 64;
 // Pass 2 (shared by all variants): out = (max(out, g - 8) + 4) / 4.
 cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip,
                              int global_max, cudaStream_t stream);

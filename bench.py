@@ -263,8 +263,7 @@ def run_own_arm(args) -> None:
     out = torch.empty(B, n_mels, N_FRAMES, device=device, dtype=out_dtype)
 
     def step(i: int) -> None:
-        b200.log_mel_spectrogram_batch(inputs[i & 1], n_mels=n_mels, out=out, variant=args.variant, out_dtype=out_dtype,
-                                       l2_chunk_clips=args.l2_chunk_clips)
+        b200.log_mel_spectrogram_batch(inputs[i & 1], n_mels=n_mels, out=out, variant=args.variant, out_dtype=out_dtype)
 
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -405,7 +404,6 @@ def main() -> None:
     ap.add_argument("--n-mels", type=int, default=80, choices=[80, 128])
     ap.add_argument("--batch", type=int, default=DEFAULT_BATCH, help="clips per step per GPU")
     ap.add_argument("--variant", default="auto", choices=["auto", "fft", "tcgen05"])
-    ap.add_argument("--l2-chunk-clips", type=int, default=0)
     ap.add_argument("--out-dtype", default="f32", choices=["f32", "f16"],
                     help="f16: the float32 result rounded to half (SURVEY 8 f3, what transcribe feeds the fp16 model)")
     ap.add_argument("--e2e-batch", type=int, default=DEFAULT_BATCH)

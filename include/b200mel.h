@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200MEL_ABI_VERSION 1
+#define B200MEL_ABI_VERSION 2
 
 /* audio constants of whisper/audio.py:13-22 */
 #define B200MEL_SAMPLE_RATE 16000
@@ -47,14 +47,15 @@ typedef enum b200mel_status {
 } b200mel_status;
 
 typedef enum b200mel_dtype {
-    B200MEL_F32 = 0, /* float32 waveform in [-1, 1]                       (audio.py:141) */
+    B200MEL_F32 = 0, /* float32 waveform, any finite range                (audio.py:141) */
     B200MEL_S16 = 1  /* int16 PCM; scaled by 1/32768 in-register          (audio.py:62)  */
 } b200mel_dtype;
 
 typedef enum b200mel_variant {
     B200MEL_VARIANT_AUTO = 0,   /* the variant ncu picked: tcgen05        */
     B200MEL_VARIANT_FFT = 1,    /* shared-memory mixed-radix (20x20) real FFT, fp32 CUDA cores */
-    B200MEL_VARIANT_TCGEN05 = 2 /* DFT-as-GEMM on tcgen05 tensor cores, 3xTF32 compensation    */
+    B200MEL_VARIANT_TCGEN05 = 2 /* folded DFT as GEMMs on tcgen05 tensor cores: fp16 hi/lo operands, the three-product
+                                   compensation of "3xTF32", fp32 accumulation, per-32-frame power-of-two pre-scale */
 } b200mel_variant;
 
 /* flags for b200mel_logmel_device / _host */
@@ -69,8 +70,8 @@ typedef enum b200mel_variant {
 
 #define B200MEL_FLAG_OUT_F16 4u    /* `out` holds IEEE half instead of float32: the values of the float32 result rounded
                                       to nearest (what transcribe.py:286 / decoding.py feed the fp16 model after their
-                                      .to(dtype)); half the write bytes.  tcgen05 variant, one max per utterance (or a
-                                      single utterance) only - otherwise B200MEL_ERR_BAD_ARGUMENT.                */
+                                      .to(dtype)); half the write bytes.  tcgen05 variant only - otherwise
+                                      B200MEL_ERR_BAD_ARGUMENT.                                                   */
 
 typedef struct b200mel_plan b200mel_plan; /* opaque: filterbank bands + FFT tables on one device */
 
@@ -105,13 +106,13 @@ size_t b200mel_workspace_bytes_tiles(int64_t batch, int64_t n_frames);
  *              B200MEL_FLAG_OUT_F16; the pointer is passed through the same parameter)
  *   workspace  device scratch of b200mel_workspace_bytes(batch), or of b200mel_workspace_bytes_tiles(batch, T)
  *              together with B200MEL_FLAG_TILE_KEYS
- *   l2_chunk_clips  reserved (0): the persistent kernel walks the batch utterance-major, so an
- *              utterance is normalised while its un-normalised values are still in L2
+ * One launch when every utterance has its own max and at most 64 x 128 frames (the kernel normalises an utterance as soon
+ * as its last tile is done, while its values are still in L2); otherwise a second, clamp-only pass follows.
  */
 int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype, int64_t batch,
                           int64_t n_samples, int64_t stride_b, const int32_t* lengths,
                           int64_t right_zero_pad, float* out, void* workspace, unsigned flags,
-                          int variant, int l2_chunk_clips, void* stream);
+                          int variant, void* stream);
 
 /* Second pass only: out = (max(out, g - 8) + 4) / 4 with g decoded from `workspace`
  * (audio.py:155-156).  Exposed for tests; b200mel_logmel_device already runs it. */
@@ -128,6 +129,12 @@ int b200mel_logmel_host(const b200mel_plan* plan, const void* audio_host, int dt
 
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t b200mel_launch_count(void);
+
+/* Diagnostic: non-zero if a hand-over between the warp roles of the tcgen05 kernel ever timed out on the current device
+ * (a protocol bug, never a property of the data).  The kernel then ran to its end instead of hanging or trapping - the
+ * caller's CUDA context stays usable - but that launch's output is garbage.  *cta (optional) receives the CTA.
+ * Synchronises the device. */
+unsigned b200mel_kernel_fault(unsigned* cta);
 
 /* Per-kernel device timing for bench.py's roofline: while enabled, every kernel launch is
  * bracketed by CUDA events on its own stream.  b200mel_profile_collect synchronises those

@@ -3,6 +3,7 @@
 // tables (csrc/tc_tables.h); the tensor-core MMAs are replaced by the exact fp16 x fp16 products they stand
 // for, read through the same operand layouts - including the neighbour's columns a leftover K step reads.
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -32,75 +33,79 @@ float b_bits(const TcTables& tab, int offset, int r, int kp) {
     return half_bits_to_float(bits);
 }
 
-// accumulator column kp of unit u for one frame: the 6 x 3 main MMAs and the 2 leftover MMAs, as issued
+// How the fp32 accumulator is modelled: 0 = exact sum of the exact fp16 x fp16 products, rounded once (the arithmetic the
+// three-product scheme stands for); 1 = a model of the hardware: after every MMA (one K step of 16 products) the
+// accumulator is truncated towards zero at the fp32 ulp of the largest addend (Fasi et al., "Numerical behavior of NVIDIA
+// tensor cores"), in the kernel's issue order - the small products first, the main product last.
+int g_accumulate_model = 0;
+
+double mma_step(double acc, const double* prod, int n) {
+    double s = acc, mag = std::fabs(acc);
+    for (int i = 0; i < n; ++i) { s += prod[i]; mag = std::max(mag, std::fabs(prod[i])); }
+    if (g_accumulate_model == 0 || mag == 0.0) return s;
+    int e;
+    std::frexp(mag, &e);                                  // mag = m 2^e, m in [0.5, 1): ulp of a 24-bit significand = 2^(e-24)
+    const double ulp = std::ldexp(1.0, e - 24);
+    return std::trunc(s / ulp) * ulp;
+}
+
+// accumulator column kp of unit u for one frame: the 6 x 2 small MMAs, the leftover correction, the 6 main MMAs and the
+// leftover main step, as issued
 float unit_column(const TcTables& tab, const std::vector<uint32_t>& tmem, int f, int u, int kp) {
     const int m = tc_unit_matrix(u);
-    double acc = 0.0;
-    for (int r = 0; r < 16 * kTcMainSteps; ++r) {
-        const double bh = b_bits(tab, tc_matrix_offset(m, 0), r, kp), bl = b_bits(tab, tc_matrix_offset(m, 1), r, kp);
-        const double ah = a_at(tmem, f, tc_hi_col(u), r), al = a_at(tmem, f, tc_lo_col(u), r);
-        acc += ah * bh + al * bh + ah * bl;
+    double acc = 0.0, prod[16];
+    for (int s = 0; s < kTcMainSteps; ++s) {
+        for (int i = 0; i < 16; ++i) prod[i] = static_cast<double>(a_at(tmem, f, tc_lo_col(u), 16 * s + i)) * b_bits(tab, tc_matrix_offset(m, 0), 16 * s + i, kp);
+        acc = mma_step(acc, prod, 16);
+        for (int i = 0; i < 16; ++i) prod[i] = static_cast<double>(a_at(tmem, f, tc_hi_col(u), 16 * s + i)) * b_bits(tab, tc_matrix_offset(m, 1), 16 * s + i, kp);
+        acc = mma_step(acc, prod, 16);
     }
-    for (int r = 0; r < 16; ++r) {   // the leftover K step reads 8 columns from tc_left_start(u)
-        const double av = a_at(tmem, f, tc_left_start(u), r);
-        acc += av * b_bits(tab, tc_left_offset(m, 0), r, kp) + av * b_bits(tab, tc_left_offset(m, 1), r, kp);
+    for (int i = 0; i < 16; ++i) prod[i] = static_cast<double>(a_at(tmem, f, tc_left_start(u), i)) * b_bits(tab, tc_left_offset(m, 1), i, kp);
+    acc = mma_step(acc, prod, 16);
+    for (int s = 0; s < kTcMainSteps; ++s) {
+        for (int i = 0; i < 16; ++i) prod[i] = static_cast<double>(a_at(tmem, f, tc_hi_col(u), 16 * s + i)) * b_bits(tab, tc_matrix_offset(m, 0), 16 * s + i, kp);
+        acc = mma_step(acc, prod, 16);
     }
+    for (int i = 0; i < 16; ++i) prod[i] = static_cast<double>(a_at(tmem, f, tc_left_start(u), i)) * b_bits(tab, tc_left_offset(m, 0), i, kp);   // the leftover K step reads 8 columns from tc_left_start(u)
+    acc = mma_step(acc, prod, 16);
     return static_cast<float>(acc);
 }
 
-constexpr TcFoldTable kFold = tc_make_fold_table();
-constexpr TcFoldWeights kFoldWeights = tc_make_fold_weights();
-constexpr TcFoldRows kFoldRows = tc_make_fold_rows();
-float head_row[2][2];     // head carry of the row-driven form, per sweep
-int g_chunk_mismatch = 0;   // set when the compile-time chunk and the table-driven chunk disagree
+constexpr TcFoldTables kFold = tc_make_fold_tables();
 
-// one sweep of one frame, stored to the emulated tensor-memory lane exactly like the kernel's fold warps do
-template <int SWEEP, int J>
-void chunk_to_tmem(const float* fr, float (&head)[2], uint32_t* lane) {
-    constexpr int u1 = 2 * SWEEP, u2 = u1 + 1;
-    uint32_t hf[4], lf[4], hs[4], ls[4];
-    tc_sweep_chunk_ct<SWEEP, J>(fr, kFoldWeights, head, hf, lf, hs, ls);
-    {   // the table-driven form of the same chunk must agree bit for bit
-        uint32_t hf2[4], lf2[4], hs2[4], ls2[4];
-        tc_sweep_chunk<SWEEP>(fr, kFold.c[SWEEP][J], hf2, lf2, hs2, ls2);
-        const int live = J < 2 * kTcMainSteps ? 4 : 3;
-        for (int q = 0; q < live; ++q)
-            if (hf[q] != hf2[q] || lf[q] != lf2[q] || hs[q] != hs2[q] || ls[q] != ls2[q]) g_chunk_mismatch = 1;
-    }
-    {   // ... and so must the row-driven form the kernel runs (its own head carry, checked chunk by chunk)
-        // a warp may start a sweep at any chunk (the kernel's two warps per quadrant start at chunks 0 and 7): the row's
-        // own head offsets must give what the carry would have
-        if (J == 0) { head_row[SWEEP][0] = fr[kFoldRows.row[SWEEP][0].head[0] / 4]; head_row[SWEEP][1] = fr[kFoldRows.row[SWEEP][0].head[1] / 4]; }
-        else if (J < kTcChunks - 1 &&
-                 (head_row[SWEEP][0] != fr[kFoldRows.row[SWEEP][J].head[0] / 4] || head_row[SWEEP][1] != fr[kFoldRows.row[SWEEP][J].head[1] / 4]))
+// one sweep of one frame at scale step `scale`, stored to the emulated tensor-memory lane exactly like the kernel's fold
+// warps do; a warp may start a sweep at any chunk (the kernel's two warps per quadrant start at chunks 0 and 7), so the
+// head carry is checked against the row's own head offsets chunk by chunk
+int g_chunk_mismatch = 0;
+void sweep_to_tmem(int sweep, int scale, const float* fr, uint32_t* lane) {
+    const int u1 = 2 * sweep, u2 = u1 + 1;
+    float head[2] = {fr[kFold.off[sweep][0].head[0] / 4], fr[kFold.off[sweep][0].head[1] / 4]};
+    for (int j = 0; j < kTcChunks; ++j) {
+        if (j > 0 && j < kTcChunks - 1 &&
+            (head[0] != fr[kFold.off[sweep][j].head[0] / 4] || head[1] != fr[kFold.off[sweep][j].head[1] / 4]))
             g_chunk_mismatch = 1;
-        uint32_t hf3[4], lf3[4], hs3[4], ls3[4];
-        tc_sweep_chunk_row(fr, kFoldRows.row[SWEEP][J], kFoldRows.sign[SWEEP], head_row[SWEEP], hf3, lf3, hs3, ls3);
-        const int live = J < 2 * kTcMainSteps ? 4 : 3;
-        for (int q = 0; q < live; ++q)
-            if (hf[q] != hf3[q] || lf[q] != lf3[q] || hs[q] != hs3[q] || ls[q] != ls3[q]) g_chunk_mismatch = 1;
-    }
-    if (J < 2 * kTcMainSteps) {
-        for (int q = 0; q < 4; ++q) {
-            lane[tc_hi_col(u1) + 4 * J + q] = hf[q]; lane[tc_lo_col(u1) + 4 * J + q] = lf[q];
-            lane[tc_hi_col(u2) + 4 * J + q] = hs[q]; lane[tc_lo_col(u2) + 4 * J + q] = ls[q];
-        }
-    } else {
-        for (int q = 0; q < 3; ++q) {
-            lane[tc_left_col(u1) + q] = hf[q]; lane[tc_left_col(u1) + 3 + q] = lf[q];
-            lane[tc_left_col(u2) + q] = hs[q]; lane[tc_left_col(u2) + 3 + q] = ls[q];
+        uint32_t hf[4], lf[4], hs[4], ls[4];
+        tc_sweep_chunk_host(fr, kFold.off[sweep][j], kFold.w[scale][sweep][j], kFold.sign[sweep], head, hf, lf, hs, ls);
+        if (j < 2 * kTcMainSteps) {
+            for (int q = 0; q < 4; ++q) {
+                lane[tc_hi_col(u1) + 4 * j + q] = hf[q]; lane[tc_lo_col(u1) + 4 * j + q] = lf[q];
+                lane[tc_hi_col(u2) + 4 * j + q] = hs[q]; lane[tc_lo_col(u2) + 4 * j + q] = ls[q];
+            }
+        } else {
+            for (int q = 0; q < 3; ++q) {
+                lane[tc_left_col(u1) + q] = hf[q]; lane[tc_left_col(u1) + 3 + q] = lf[q];
+                lane[tc_left_col(u2) + q] = hs[q]; lane[tc_left_col(u2) + 3 + q] = ls[q];
+            }
         }
     }
 }
-template <int SWEEP, int... J>
-void sweep_seq(const float* fr, uint32_t* lane, std::integer_sequence<int, J...>) {
-    float head[2];
-    tc_sweep_heads<SWEEP>(fr, head);
-    (chunk_to_tmem<SWEEP, J>(fr, head, lane), ...);
-}
-void sweep_to_tmem(int sweep, const float* fr, uint32_t* lane) {
-    if (sweep == 0) sweep_seq<0>(fr, lane, std::make_integer_sequence<int, kTcChunks>{});
-    else sweep_seq<1>(fr, lane, std::make_integer_sequence<int, kTcChunks>{});
+
+// scale step of lane quadrant q of the staged tile: the largest |sample| its 32 frames read (samples 0 .. 5359 from the
+// quadrant's first row - what the kernel's E sweep tracks)
+int quadrant_scale(const float* s_audio, int q) {
+    float m = 0.f;
+    for (int i = 0; i < 31 * kHop + kNFFT; ++i) m = tc_abs_max(m, s_audio[(32 * q + i / kHop) * kTcRowPitch + i % kHop]);
+    return tc_scale_index(float_bits(m));
 }
 
 template <int NM, int U>
@@ -127,7 +132,7 @@ int run(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
     const int tiles = (n_frames + kTcTileFrames - 1) / kTcTileFrames;
     if (valid > n_samples) valid = n_samples;
 
-    std::vector<float> s_audio(kTcAudioWords + 8, 0.f);
+    std::vector<float> s_audio((kTcAudioRows + 1) * kTcRowPitch + 8, 0.f);
     std::vector<uint32_t> tmem(kTcTileFrames * 512, 0u);   // tensor memory: [lane][column], zero-initialised like the kernel
     uint32_t clip_key = 0;
 
@@ -143,11 +148,13 @@ int run(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
             }
             s_audio[(i / kHop) * kTcRowPitch + i % kHop] = v;
         }
+        int scale[4];
+        for (int q = 0; q < 4; ++q) scale[q] = quadrant_scale(s_audio.data(), q);
         for (int f = 0; f < kTcTileFrames; ++f) {
             const float* fr = s_audio.data() + f * kTcRowPitch;
             uint32_t* lane = tmem.data() + f * 512;
-            sweep_to_tmem(0, fr, lane);
-            sweep_to_tmem(1, fr, lane);
+            sweep_to_tmem(0, scale[f / 32], fr, lane);
+            sweep_to_tmem(1, scale[f / 32], fr, lane);
         }
         for (int f = 0; f < kTcTileFrames && t0 + f < n_frames; ++f) {
             float acc0[L::acc_size(0)] = {0.f}, acc1[L::acc_size(1)] = {0.f};
@@ -165,7 +172,7 @@ int run(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
                 float s = 0.f;
                 if (m < L::low_mels) s += acc0[m];
                 if (m >= L::high_base) s += acc1[m - L::high_base];
-                const float lg = log10_clamped(s);
+                const float lg = log10_clamped(s * kFold.unscale[scale[f / 32]]);
                 out[static_cast<int64_t>(m) * n_frames + t0 + f] = lg;
                 clip_key = std::max(clip_key, max_key_encode(lg));
             }
@@ -179,6 +186,8 @@ int run(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
 }
 
 }  // namespace
+
+extern "C" void emul_tc_accumulate_model(int model) { g_accumulate_model = model; }
 
 extern "C" int emul_tc_logmel(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
                               int n_mels, const float* filters, float* out, int do_normalise) {
@@ -197,21 +206,24 @@ extern "C" int emul_tc_frame_spectrum(const float* frame400, double* re, double*
         build_tc_tables(80, dummy.data(), &tab);   // the matrices do not depend on the filters (status ignored)
         built = true;
     }
-    std::vector<float> s_audio(3 * kTcRowPitch, 0.f);
+    std::vector<float> s_audio(3 * kTcRowPitch + 8, 0.f);
     for (int n = 0; n < kNFFT; ++n) s_audio[tc_off(n)] = frame400[n];
     std::vector<uint32_t> tmem(512, 0u);
-    sweep_to_tmem(0, s_audio.data(), tmem.data());
-    sweep_to_tmem(1, s_audio.data(), tmem.data());
+    float m = 0.f;
+    for (int n = 0; n < kNFFT; ++n) m = tc_abs_max(m, frame400[n]);
+    const int scale = tc_scale_index(float_bits(m));
+    sweep_to_tmem(0, scale, s_audio.data(), tmem.data());
+    sweep_to_tmem(1, scale, s_audio.data(), tmem.data());
     for (int u = 0; u < kTcUnits; ++u) {
         for (int kp = 0; kp < kTcBinsPerUnit; ++kp) {
             const int bin = tc_unit_bin(u, kp);
-            const double v = static_cast<double>(unit_column(tab, tmem, 0, u, kp)) / (kTcDataScale * kTcMatrixScale);
+            const double v = static_cast<double>(unit_column(tab, tmem, 0, u, kp)) / (static_cast<double>(tc_pow2(tc_scale_exponent(scale))) * kTcMatrixScale);
             if (u < 2) re[bin] = v; else im_abs[bin] = v < 0 ? -v : v;
         }
     }
     return 0;
 }
 
-// 1 when any chunk computed so far differed between the compile-time form (what the kernel runs) and the
-// table-driven form of the fold (tc_core.cuh)
+// 1 when the sample a sweep chunk hands on to the next one ever differed from the head sample the fold table names for
+// that chunk (a warp may start a sweep at any chunk)
 extern "C" int emul_tc_chunk_mismatch() { return g_chunk_mismatch; }

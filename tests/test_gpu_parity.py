@@ -298,29 +298,101 @@ def test_runs_on_the_current_stream(b200):
     assert torch.equal(y, ref)
 
 
+def _full_size_report(tag, got, ref, f64):
+    """Worst deviations over EVERY value of a full-size batch; returns (|gpu - ref|, |gpu - f64|, |ref - f64|) maxima and the
+    mask of values where the GPU result is more than TOL from the reference."""
+    d_ref, d_f64, e_ref = np.abs(got - ref), np.abs(got - f64), np.abs(ref - f64)
+    far = d_ref > TOL
+    print(f"{tag}: {got.size / 1e6:.1f} M values  |gpu - ref| {d_ref.max():.3e} ({int(far.sum())} values > {TOL:g})  "
+          f"|gpu - f64| {d_f64.max():.3e}  |ref - f64| {e_ref.max():.3e}")
+    return d_ref, d_f64, e_ref, far
+
+
+def _assert_full_size_parity(tag, got, ref, f64, shipped):
+    """The bar at full size.  Every value of the GPU result is within 1e-4 of the float64 statement of the reference's
+    formulas, and all but a handful in 10^8 within 1e-4 of the reference's own fp32 result.  For the kernel that ships
+    (tcgen05) the handful is pinned down: it happens only where the reference ITSELF is more than 5e-5 from float64
+    (isolated values whose mel power is ~1e-7 of the frame's energy: any two fp32 evaluations differ there), and there
+    the GPU value is the closer one to float64."""
+    d_ref, d_f64, e_ref, far = _full_size_report(tag, got, ref, f64)
+    assert d_f64.max() <= TOL, f"{tag}: {d_f64.max():.3e} from float64"
+    assert far.sum() <= 1e-6 * got.size
+    assert d_ref.max() <= 1.5 * TOL
+    if shipped:
+        assert np.all(e_ref[far] > 5e-5), f"{tag}: more than {TOL:g} from a reference value that is itself within 5e-5 of float64"
+        assert np.all(d_f64[far] < e_ref[far]), f"{tag}: further from float64 than the reference"
+
+
 @pytest.mark.parametrize("n_mels", [80, 128])
-def test_full_size_batch_properties(b200, n_mels):
-    # BASELINE configs 2 / 3 at full size: 256 clips x 30 s, checked through size-independent properties
+def test_full_size_batch_every_clip(b200, n_mels, default_variant):
+    """BASELINE configs 2 / 3 at full size - 256 clips x 30 s, the batch bench.py times (seed 1234) - EVERY clip against
+    the oracle (fp32 port per utterance and float64), plus the size-independent properties."""
     gen = torch.Generator(device=DEV).manual_seed(1234)
     audio = (0.1 * torch.randn(256, 480000, generator=gen, device=DEV)).clamp_(-1, 1)
-    audio[17] = audio[3]            # replicas of one clip at different batch positions
-    audio[200] = audio[3]
     out = b200.log_mel_spectrogram_batch(audio, n_mels=n_mels)
     assert tuple(out.shape) == (256, n_mels, 3000)
-    assert torch.equal(out[17], out[3]) and torch.equal(out[200], out[3])
-    # chunking is invisible: any L2 chunk size gives the same bytes
-    assert torch.equal(b200.log_mel_spectrogram_batch(audio, n_mels=n_mels, l2_chunk_clips=7), out)
+    host = audio.cpu()
+    ref = orc.logmel_f32_port_per_utterance(host, n_mels).numpy()
+    f64 = np.stack([orc.logmel_f64(c, n_mels) for c in host.numpy()])
+    _assert_full_size_parity(f"config {'2' if n_mels == 80 else '3'} [{default_variant}]", out.cpu().numpy(), ref, f64,
+                             shipped=default_variant == "tcgen05")
+    # replicas of one clip at other batch positions, and alone: the same bytes
+    audio[17] = audio[3]
+    audio[200] = audio[3]
+    again = b200.log_mel_spectrogram_batch(audio, n_mels=n_mels)
+    assert torch.equal(again[17], out[3]) and torch.equal(again[200], out[3]) and torch.equal(again[3], out[3])
+    assert torch.equal(b200.log_mel_spectrogram_batch(audio[3:4], n_mels=n_mels)[0], out[3])
     # dynamic range: every utterance spans at most 8 decades => (max - min) <= 2 after (x+4)/4
     mx, mn = out.amax(dim=(1, 2)), out.amin(dim=(1, 2))
     assert torch.all(mx - mn <= 2.0 + 1e-6) and torch.isfinite(out).all()
-    # idempotence of the call and independence from the rest of the batch
-    assert torch.equal(b200.log_mel_spectrogram_batch(audio[3:4], n_mels=n_mels)[0], out[3])
-    # spot-check three clips against the oracle
-    for i in (0, 3, 255):
-        assert _maxerr(out[i], orc.logmel_f32_port(audio[i].cpu(), n_mels)) <= TOL
     # checksum of checksums is reproducible run to run
-    again = b200.log_mel_spectrogram_batch(audio, n_mels=n_mels)
-    assert float(out.double().sum(dim=(1, 2)).sum()) == float(again.double().sum(dim=(1, 2)).sum())
+    third = b200.log_mel_spectrogram_batch(audio, n_mels=n_mels)
+    assert float(again.double().sum(dim=(1, 2)).sum()) == float(third.double().sum(dim=(1, 2)).sum())
+
+
+def test_variable_length_epoch_every_clip(b200, default_variant):
+    """BASELINE config 4: a 1,737-clip "epoch" (data/custom_train.csv) of 1-30 s clips in train batches of 16 and val
+    batches of 8 (speech_disorder/config.py:15-16), zero-padded to 30 s as dataset.py:85 does - every clip of a sample of
+    those batches against the oracle, padded rows and the `lengths` fast path alike."""
+    lens = signals.variable_lengths(1737)
+    batches = [(16, list(range(0, 96))), (16, list(range(1728, 1737))), (8, list(range(800, 840)))]
+    worst = 0.0
+    for bs, idx in batches:
+        for b0 in range(0, len(idx), bs):
+            ids = idx[b0:b0 + bs]
+            clips = np.zeros((len(ids), 480000), np.float32)
+            for r, i in enumerate(ids):
+                clips[r, :lens[i]] = signals.make_signal("gauss", int(lens[i]), 5000 + i)
+            ref = orc.logmel_f32_port_per_utterance(torch.from_numpy(clips), 80).numpy()
+            x = torch.from_numpy(clips).to(DEV)
+            padded = b200.log_mel_spectrogram_batch(x, n_mels=80)
+            fast = b200.log_mel_spectrogram_batch(x, n_mels=80, lengths=torch.from_numpy(lens[ids]))
+            assert torch.equal(padded, fast)
+            err = float(np.abs(padded.cpu().numpy() - ref).max())
+            worst = max(worst, err)
+            assert err <= TOL, (bs, ids[0], err)
+    print(f"config 4 [{default_variant}]: worst |gpu - ref| {worst:.3e} over {sum(len(i) for _, i in batches)} clips")
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1e-4, 1e-2, 100.0, 32768.0, 1e6])
+def test_amplitude_ladder(b200, scale):
+    """The reference takes any float32 waveform (e.g. int16-valued samples that were never divided by 32768): so does
+    this front-end, with the same accuracy at every amplitude."""
+    clips = np.stack([(scale * np.random.default_rng(50 + i).standard_normal(80000)).astype(np.float32) for i in range(4)])
+    ref = orc.logmel_f32_port_per_utterance(torch.from_numpy(clips), 80)
+    got = b200.log_mel_spectrogram_batch(torch.from_numpy(clips).to(DEV), n_mels=80)
+    assert torch.isfinite(got).all()
+    assert _maxerr(got, ref) <= TOL
+
+
+def test_loud_and_quiet_inside_one_utterance(b200):
+    """1 s at full scale, then 4 s at -60 dB (inside the 80 dB window): the quiet part keeps its relative precision."""
+    rng = np.random.default_rng(7)
+    for quiet in (1e-3, 3e-4):
+        clip = (0.5 * np.concatenate([rng.standard_normal(16000), quiet * rng.standard_normal(64000)])).astype(np.float32)
+        got = b200.log_mel_spectrogram(torch.from_numpy(clip).to(DEV), 80).cpu()
+        assert _maxerr(got, orc.logmel_f32_port(clip, 80)) <= TOL
+        assert float(np.abs(got.numpy() - orc.logmel_f64(clip, 80)).max()) <= TOL
 
 
 def test_large_batch_indexing(b200):
