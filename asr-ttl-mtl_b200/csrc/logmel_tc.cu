@@ -62,7 +62,7 @@ constexpr uint32_t kWaitHintNs = 20000;      // suspend-time hint of one try_wai
 constexpr int kTraceTiles = 8, kTraceEvents = 16, kTraceRoles = 6;
 constexpr int kTraceWords = kTraceRoles * kTraceTiles * kTraceEvents + 8;
 #if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
-// (bring-up switches ride in the upper bits of trace_first: 0x200 = count without the fence, 0x400 = no L2 prefetch - measurement only, wrong results for out-of-range data / the clamp path)
+// (bring-up switches ride in the upper bits of trace_first: 0x200 = count without the fence, 0x400 = no L2 prefetch, 0x800 = bulk instead of tensor L2 prefetch - measurement only, wrong results for out-of-range data / the clamp path)
 #define TC_DEBUG_FLAG(bit) ((trace_first_arg & (bit)) != 0)
 #else
 #define TC_DEBUG_FLAG(bit) false
@@ -937,7 +937,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         };
         auto prefetch_half = [&](const TileCoord& tp) {
             if (TC_DEBUG_FLAG(0x400)) return;
-            if (half_mode<InT>(a, tma_rows, tp, half) == kModeTma) tma_prefetch_half(&audio_map, tp, half);
+            if (half_mode<InT>(a, tma_rows, tp, half) == kModeTma && !TC_DEBUG_FLAG(0x800)) tma_prefetch_half(&audio_map, tp, half);
             else prefetch_half_l2<InT>(a, tp, half);
         };
         uint32_t parity = 0, full_parity = 0;

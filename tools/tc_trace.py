@@ -8,7 +8,9 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import asr_ttl_mtl_b200 as b
 n_mels = int(os.environ.get("N_MELS", "80"))
-x = [(0.1 * torch.randn(256, 480000, device="cuda")) for _ in range(2)]
+B = int(os.environ.get("CLIPS", "256"))
+x = [(0.1 * torch.randn(B, 480000, device="cuda")) for _ in range(1 if os.environ.get("SAME") else 2)]
+x = x * 2
 if os.environ.get("PCM"):
     x = [(v * 32768).round().clamp(-32768, 32767).to(torch.int16) for v in x]
 for i in range(3):
@@ -27,4 +29,4 @@ if not os.environ.get("B200MEL_TC_TRACE"):
         b.log_mel_spectrogram_batch(x[i & 1], n_mels=n_mels, variant="tcgen05", out=y)
     torch.cuda.synchronize()
     ms, n = _native.profile_collect()["tcgen05_pass"]
-    print(f"flags={os.environ.get('B200MEL_TC_FLAGS', '0')} n_mels={n_mels} pcm={bool(os.environ.get('PCM'))}: {ms / n:.4f} ms per 256 clips (kernel events, {n} launches)")
+    print(f"flags={os.environ.get('B200MEL_TC_FLAGS', '0')} n_mels={n_mels} pcm={bool(os.environ.get('PCM'))}: {ms / n:.4f} ms per {B} clips (kernel events, {n} launches)")
