@@ -287,11 +287,10 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
         B200_CUDA(cudaMemsetAsync(a.tile_keys, 0, static_cast<size_t>(batch) * tc_tiles_per_clip(n_frames) * 2 * sizeof(uint32_t), stream));
     }
     a.global_max = global_max;
-    // one max per utterance (or a single utterance, where the call's max is the utterance's): normalised inside the
-    // front-end kernel by the CTA that finishes the utterance - unless the utterance is so long that this would be a
-    // serial tail (whole-file transcription): then pass 2 normalises at full bandwidth.
-    const bool short_enough = variant == B200MEL_VARIANT_TCGEN05 ? tc_tiles_per_clip(n_frames) <= kTcMaxFusedNormTiles : tiles_per_clip <= kMaxFusedNormTiles;
-    a.fused_norm = ((!global_max || batch == 1) && short_enough) ? 1 : 0;
+    // FFT variant: one max per utterance (or a single utterance, where the call's max is the utterance's) is normalised
+    // inside the kernel by the CTA that finishes the utterance, unless the utterance is very long; the tcgen05 variant
+    // always runs its finish kernel right behind
+    a.fused_norm = (variant == B200MEL_VARIANT_FFT && (!global_max || batch == 1) && tiles_per_clip <= kMaxFusedNormTiles) ? 1 : 0;
     a.n_rows = plan->n_rows;
     a.tables = plan->d_tables;
     if (a.out_f16 && variant != B200MEL_VARIANT_TCGEN05) return B200MEL_ERR_BAD_ARGUMENT;
@@ -299,10 +298,8 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
         B200_CUDA(launch_tc_pass1(a, plan->d_tc_tables, dtype, stream));
     else
         B200_CUDA(launch_fft_fused(a, dtype, stream));
-    if (!a.fused_norm) {
-        if (variant == B200MEL_VARIANT_TCGEN05) B200_CUDA(launch_tc_clamp(out, a.out_f16, keys, batch, elems_per_clip, global_max, stream));
-        else B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, global_max, stream));
-    }
+    if (variant == B200MEL_VARIANT_TCGEN05) B200_CUDA(launch_tc_finish(a, stream));
+    else if (!a.fused_norm) B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, global_max, stream));
     return B200MEL_OK;
 }
 

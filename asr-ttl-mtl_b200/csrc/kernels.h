@@ -37,20 +37,17 @@ struct LogmelArgs {
 // FFT variant, one persistent launch: log10 mel + per-utterance max keys (+ in-place normalise when
 // a.fused_norm).  The counters in `a` must be zero when the kernel starts.
 cudaError_t launch_fft_fused(const LogmelArgs& a, int dtype, cudaStream_t stream);
-// tcgen05 variant (the folded DFT as GEMMs on the tensor cores), one persistent launch: with a.fused_norm the
-// finished log-mel, otherwise (log10 mel + 4) / 4 and the max keys for launch_tc_clamp.  The counters and keys in `a`
+// tcgen05 variant (the folded DFT as GEMMs on the tensor cores), one persistent launch: (log10 mel + 4) / 4 and the
+// extremes of every utterance and tile, for launch_tc_finish (a.fused_norm is not used).  The counters and keys in `a`
 // must be zero when the kernel starts.  tables: device copy of the constant matrices.
 cudaError_t launch_tc_pass1(const LogmelArgs& a, const TcTables* tables, int dtype, cudaStream_t stream);
-// Clamp pass for the calls the tcgen05 kernel does not normalise itself: out = max(out, ((g - 8) + 4) / 4) on its already
-// rescaled values (float32 or half).
-cudaError_t launch_tc_clamp(void* out, int out_f16, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip, int global_max,
-                            cudaStream_t stream);
+// Finish kernel of the tcgen05 variant, launched right behind launch_tc_pass1 on the same stream: applies the clamp at
+// max - 8 tile by tile from the extremes pass 1 left (float32 or half output; one max per utterance or per call).
+cudaError_t launch_tc_finish(const LogmelArgs& a, cudaStream_t stream);
 // Code (0 = none) and CTA of a hand-over inside the tcgen05 kernel that timed out (a protocol bug: the kernel then ran to
 // its end with garbage in that launch's output instead of hanging); synchronises the device.
 unsigned tc_kernel_fault(unsigned* cta);
-// an utterance of more tiles than this is normalised by the pass-2 kernel (the in-kernel normaliser takes an utterance
-// with two warps)
-constexpr int64_t kTcMaxFusedNormTiles = 64;
+
 // Pass 2 (shared by all variants): out = (max(out, g - 8) + 4) / 4.
 cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip,
                              int global_max, cudaStream_t stream);

@@ -25,18 +25,16 @@
 //     warps           into registers at once (tcgen05.ld), release the accumulator, and add w d^2 to the mels
 //                     of each bin - mel structure and weights are compile-time constants (FFMA immediates),
 //                     partial sums in registers; after the 4th unit: 2^-2k, log10(max(., 1e-10)), (x + 4) / 4, 128-byte
-//                     coalesced row stores, the utterance's and the tile's extremes (warp REDUX + atomicMax), and -
-//                     one tile late, behind a fence - the utterance's count of finished tiles;
-//   2 normaliser    : the warp that counts an utterance's LAST tile hands the utterance to its own CTA's normaliser
-//     warps           warps (a queue in shared memory): they decide from the utterance's and each tile's extremes what
-//                     the clamp at max - 8 does to the tile: nothing (the usual case), a constant fill (digital
-//                     silence, zero padding) or a clamp in place while the tile is still in L2 - so the front-end is
-//                     one launch whose DRAM traffic is the algorithmic read + write.  No CTA ever waits for another
-//                     one: the kernel makes progress with any number of co-resident CTAs.
+//                     coalesced row stores, the utterance's and the tile's extremes (warp REDUX + atomicMax).
+// No CTA ever waits for another one - there is no cross-CTA hand-over at all - so the kernel makes progress with any
+// number of co-resident CTAs.  What is left of the normalisation, the clamp at max - 8, needs every tile of an utterance:
+// the FINISH kernel right behind (tc_finish_kernel, a warp per tile) decides from the utterance's and the tile's extremes
+// what the clamp does to the tile: nothing (the usual case: it reads three words and moves on), a constant fill (digital
+// silence / zero padding - tiles whose samples are all zero are not even stored by the epilogue) or a clamp in place while
+// the tile is still in L2.  For speech-like input the DRAM traffic stays the algorithmic read + write.
 // Tensor memory is exactly full: 408 operand columns (4 units x [hi | lo], tc_core.cuh) + 104 accumulator; so is shared
 // memory (DFT matrices + the two half tiles).  The hot code of all roles has to fit the 32 KB instruction cache: loops
 // over table rows instead of unrolled code wherever the work is regular.
-// (One max over a whole multi-utterance call, or an utterance of more than 64 tiles: the shared pass-2 kernel normalises.)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -51,7 +49,7 @@ namespace b200mel {
 
 namespace {
 
-constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16, kWarpNorm = 17;   // normalisers: warps 17, 18 (19 idles)
+constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16;   // (warps 17-19 complete the warpgroup and idle)
 constexpr int kTcWarps = 20;
 constexpr int kTcThreads = kTcWarps * 32;   // 640
 constexpr uint32_t kSpinLimit = 1u << 17;    // x 20 us hint = 2.6 s: a protocol bug ends the kernel instead of hanging the device
@@ -239,17 +237,9 @@ struct TcBarriers {
     uint64_t d_full, d_empty;
 };
 
-// Utterances whose last tile was counted by one of this CTA's epilogue warps, waiting for the CTA's normaliser warps.
-constexpr uint32_t kQueueSlots = 32;
-struct TcNormQueue {
-    uint32_t tail;                    // next slot a producer (epilogue warp) takes
-    uint32_t head[2];                 // per normaliser warp: entries it has finished with
-    uint32_t producers_done;          // epilogue warps that will push no more
-    uint32_t seq[kQueueSlots];        // slot s of lap n is readable once seq == entry index + 1
-    uint32_t clip[kQueueSlots];
-};
-// what the folds tell the epilogue about a tile: the scale step of each lane quadrant, [tile parity][quadrant]
-struct TcTileInfo { uint32_t scale[2][4]; uint32_t quad_max[4][2]; uint32_t released[2]; };
+// what the folds tell the epilogue about a tile: the scale step of each lane quadrant and whether all its samples are
+// zero, [tile parity][quadrant]
+struct TcTileInfo { uint32_t scale[2][4]; uint32_t silent[2][4]; uint32_t quad_max[4][2]; uint32_t released[2]; };
 
 // ---- normaliser -------------------------------------------------------------------------------------
 // clamp of an already rescaled value y = (lg + 4) / 4 at floor_y = ((g - 8) + 4) / 4 (NaN when the max is NaN, as in
@@ -322,78 +312,6 @@ __device__ __forceinline__ void normalise_tile_tc(OutT* __restrict__ tile_out, i
             OutT* q = tile_out + (i / frames) * pitch + i % frames;
             out_store(q, clamp_scaled(out_load(q), g));
         }
-    }
-}
-
-// An epilogue warp (one lane) hands a finished utterance to the CTA's normaliser warps.
-__device__ __forceinline__ void queue_push(TcNormQueue* q, uint32_t clip, volatile uint32_t* abort) {
-    const uint32_t slot = atomicAdd(&q->tail, 1u);
-    // the ring holds 32 finished utterances; a CTA counts an utterance's last tile once in ~150 tiles
-    while (true) {
-        const uint32_t h0 = *reinterpret_cast<volatile uint32_t*>(&q->head[0]), h1 = *reinterpret_cast<volatile uint32_t*>(&q->head[1]);
-        const uint32_t oldest = static_cast<int32_t>(h0 - h1) < 0 ? h0 : h1;
-        if (slot - oldest < kQueueSlots || *abort != 0) break;
-        __nanosleep(200);
-    }
-    *reinterpret_cast<volatile uint32_t*>(&q->clip[slot % kQueueSlots]) = clip;
-    __threadfence_block();
-    *reinterpret_cast<volatile uint32_t*>(&q->seq[slot % kQueueSlots]) = slot + 1u;
-}
-
-// The normaliser warps' loop.  Warp `w` of the two takes every second tile of each utterance.
-template <int NM, typename OutT>
-__device__ __forceinline__ void normaliser_role(const LogmelArgs& a, TcNormQueue* q, volatile uint32_t* abort, int w, int lane, int tiles_per_clip) {
-    uint32_t head = 0;
-    while (true) {
-        int have = 0;
-        if (lane == 0) {
-            while (true) {
-                if (*reinterpret_cast<volatile uint32_t*>(&q->seq[head % kQueueSlots]) == head + 1u) { have = 1; break; }
-                if (*reinterpret_cast<volatile uint32_t*>(&q->producers_done) == 8u && *reinterpret_cast<volatile uint32_t*>(&q->tail) == head) {
-                    // (the pushes of a producer that is done are all visible: it fences before it says so)
-                    if (*reinterpret_cast<volatile uint32_t*>(&q->seq[head % kQueueSlots]) == head + 1u) have = 1;
-                    break;
-                }
-                if (*abort != 0) break;
-                __nanosleep(500);
-            }
-        }
-        have = __shfl_sync(0xffffffffu, have, 0);
-        if (!have) break;
-        __threadfence();                         // acquire: the rows and the extremes of the whole utterance are visible
-        const int64_t clip = *reinterpret_cast<volatile uint32_t*>(&q->clip[head % kQueueSlots]);
-        const float g = max_key_decode(__ldcg(a.max_keys + clip));
-        const float floor_lg = g - 8.0f;
-        const float smallest = max_key_decode(~__ldcg(a.min_keys + clip));
-        if (!(smallest >= floor_lg)) {           // something in the utterance is below the clamp (or the max is NaN)
-            const float floor_y = ((g - 8.0f) + 4.0f) * 0.25f;
-            // lane l looks at tile w + 2 l (an utterance normalised here has at most 64 tiles)
-            const int t = w + 2 * lane;
-            int action = 0;                      // 0: leave the tile alone, 1: clamp it in place, 2: fill it with the clamp value
-            if (t < tiles_per_clip) {
-                action = 1;
-                if (a.tile_keys != nullptr) {
-                    const uint32_t* tk = a.tile_keys + 2 * (clip * tiles_per_clip + t);
-                    const float tile_max = max_key_decode(__ldcg(tk)), tile_min = max_key_decode(~__ldcg(tk + 1));
-                    if (tile_min >= floor_lg) action = 0;          // this tile is wholly above the clamp
-                    else if (tile_max < floor_lg) action = 2;      // wholly below it (digital silence, zero padding)
-                }
-            }
-            unsigned todo = __ballot_sync(0xffffffffu, action != 0);
-            while (todo != 0) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const bool fill = __shfl_sync(0xffffffffu, action, src) == 2;
-                const int t0 = (w + 2 * src) * kTcTileFrames;
-                const int frames = a.n_frames - t0 < kTcTileFrames ? a.n_frames - t0 : kTcTileFrames;
-                OutT* tile_out = reinterpret_cast<OutT*>(a.out) + clip * NM * static_cast<int64_t>(a.n_frames) + t0;
-                if (fill) fill_tile_tc<NM, OutT>(tile_out, a.n_frames, frames, floor_y, lane);
-                else normalise_tile_tc<NM, OutT>(tile_out, a.n_frames, frames, floor_y, lane);
-            }
-        }
-        ++head;
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&q->head[w]) = head;
     }
 }
 
@@ -715,7 +633,7 @@ static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) =
 // ---- epilogue ---------------------------------------------------------------------------------------
 template <int NM, int HALF, typename OutT>
 __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* trace, const int trace_first_arg, TcBarriers* bars,
-                                              TcNormQueue* queue, const TcTileInfo* info, TcAbort ab, float* s_straddle,
+                                              const TcTileInfo* info, TcAbort ab, float* s_straddle,
                                               uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
     using L = TcEpilogueLayout<NM>;
     constexpr int ACC = L::acc_size(HALF);
@@ -725,20 +643,6 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
     for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
     const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol + L::col0(HALF);
     uint32_t d_parity = 0, buf = 0;
-    // Fused normalisation: this warp's share of an utterance is counted one tile late - behind a gpu-scope fence that
-    // by then has nothing left to wait for - so whoever counts the utterance's last share may read every row and every
-    // extreme of it.
-    int64_t pending_clip = -1;
-    const uint32_t need = 8u * static_cast<uint32_t>(tiles_per_clip);
-    auto count_pending = [&]() {
-        if (!TC_DEBUG_FLAG(0x200)) __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-            const uint32_t before = atomicAdd(a.done_counters + pending_clip, 1u);
-            if (before + 1u == need) queue_push(queue, static_cast<uint32_t>(pending_clip), ab.flag);
-        }
-        pending_clip = -1;
-    };
     const int64_t my_tiles = static_cast<int64_t>(blockIdx.x) < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TileCoord prev{0, 0};
     TileCursor cursor(tiles_per_clip);
@@ -751,6 +655,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
         prev = cursor.at;
         cursor.advance();
         float unscale = 1.0f;
+        bool silent = false;
 #pragma unroll 1
         for (int u = 0; u < kTcUnits; ++u) {
             float d[L::cols(HALF)];
@@ -760,7 +665,12 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
             tc_fence_after();
             tmem_ld_cols<L::cols(HALF)>(d_addr, d);
             // the quadrant's scale step was written before the folds released the E operand, i.e. before this unit's MMAs
-            if (u == 0) unscale = c_fold.unscale[*reinterpret_cast<const volatile uint32_t*>(&info->scale[k & 1][quad])];
+            if (u == 0) {
+                unscale = c_fold.unscale[*reinterpret_cast<const volatile uint32_t*>(&info->scale[k & 1][quad])];
+                // a tile whose samples are ALL zero (zero padding) is not stored: the finish kernel fills it (it needs per-tile keys for that)
+                const volatile uint32_t* z = info->silent[k & 1];
+                silent = a.tile_keys != nullptr && (z[0] & z[1] & z[2] & z[3]) != 0u;
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
@@ -772,7 +682,6 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
             if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
             if (u == kTcUnits - 1) {
                 // ---- finish this tile ----
-                if (pending_clip >= 0) count_pending();        // the tile before it
                 if (quad == 0) TC_TRACE(4 + HALF, ti, 13);
                 // join the mels that straddle the split: half 1 hands its partial sums to half 0
                 float* strad = s_straddle + ((buf * 4 + quad) * 3) * 32 + lane;
@@ -789,7 +698,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
                 if (quad == 0) TC_TRACE(4 + HALF, ti, 14);
                 // log10 clamp, coalesced row stores (lane = frame), utterance extremes
                 const int f = quad * 32 + lane, t = prev.t0 + f;
-                const bool live = t < a.n_frames;
+                const bool live = t < a.n_frames && !silent;
                 constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
                 const int64_t pitch = a.n_frames;
                 OutT* const out = reinterpret_cast<OutT*>(a.out) + (prev.clip * NM + m_begin) * pitch + t;
@@ -828,30 +737,20 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
                 if (quad == 0) TC_TRACE(4 + HALF, ti, 15);
                 uint32_t key = live ? max_key_encode(mx) : 0u;
                 key = __reduce_max_sync(0xffffffffu, key);
-                if (a.fused_norm) {
-                    uint32_t inv = live ? ~max_key_encode(mn) : 0u;
-                    inv = __reduce_max_sync(0xffffffffu, inv);
-                    if (lane == 0) {
-                        atomicMax(a.max_keys + (a.global_max ? 0 : prev.clip), key);
-                        atomicMax(a.min_keys + prev.clip, inv);
-                        if (a.tile_keys != nullptr) {   // the tile's own extremes: lets the clamp path skip or fill whole tiles
-                            uint32_t* tk = a.tile_keys + 2 * (static_cast<int64_t>(blockIdx.x) + k * gridDim.x);
-                            atomicMax(tk, key);
-                            atomicMax(tk + 1, inv);
-                        }
-                    }
-                    pending_clip = prev.clip;   // counted at the next finish
-                } else if (lane == 0) {
+                uint32_t inv = live ? ~max_key_encode(mn) : 0u;
+                inv = __reduce_max_sync(0xffffffffu, inv);
+                if (lane == 0 && key != 0u) {       // (key 0: nothing stored - frames past the end, or a silent tile)
                     atomicMax(a.max_keys + (a.global_max ? 0 : prev.clip), key);
+                    atomicMax(a.min_keys + prev.clip, inv);
+                    if (a.tile_keys != nullptr) {   // the tile's own extremes: lets the finish kernel skip or fill whole tiles
+                        uint32_t* tk = a.tile_keys + 2 * (static_cast<int64_t>(blockIdx.x) + k * gridDim.x);
+                        atomicMax(tk, key);
+                        atomicMax(tk + 1, inv);
+                    }
                 }
                 if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
             }
         }
-    }
-    if (pending_clip >= 0) count_pending();
-    if (a.fused_norm) {
-        __threadfence_block();
-        if (lane == 0) atomicAdd(&queue->producers_done, 1u);
     }
 }
 
@@ -864,7 +763,6 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     float* s_audio = reinterpret_cast<float*>(smem_raw + kSmemAudio);
     float* s_straddle = reinterpret_cast<float*>(smem_raw + kSmemStraddle);
     __shared__ __align__(8) TcBarriers bars;
-    __shared__ TcNormQueue queue;
     __shared__ TcTileInfo info;
     __shared__ uint32_t s_tmem, s_abort;
     const TcAbort ab{&s_abort};
@@ -887,8 +785,6 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
         mbar_init(&bars.d_full, 1);
         mbar_init(&bars.d_empty, 8);
-        queue.tail = 0; queue.head[0] = queue.head[1] = 0; queue.producers_done = 0;
-        for (uint32_t i = 0; i < kQueueSlots; ++i) { queue.seq[i] = 0; queue.clip[i] = 0; }
         s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -993,12 +889,15 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                     // (the partner reads this tile's value before either warp can write the next tile's: the O sweep is between)
                     const uint32_t other = *reinterpret_cast<volatile uint32_t*>(&info.quad_max[quad][part ^ 1]);
                     const uint32_t want = static_cast<uint32_t>(tc_scale_index(mine > other ? mine : other));
-                    if (want != scale) {
+                    if (want != scale && !TC_DEBUG_FLAG(0x4000)) {
                         scale = want;
                         sweep_store<false>(0, scale, j0, j1, fr, lane_addr);
                     }
                     last_scale = scale;
-                    if (part == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(&info.scale[ti & 1][quad]) = scale;
+                    if (part == 0 && lane == 0) {
+                        *reinterpret_cast<volatile uint32_t*>(&info.scale[ti & 1][quad]) = scale;
+                        *reinterpret_cast<volatile uint32_t*>(&info.silent[ti & 1][quad]) = (mine | other) == 0u ? 1u : 0u;
+                    }
                 } else {
                     sweep_store<false>(1, scale, j0, j1, fr, lane_addr);
                 }
@@ -1034,8 +933,8 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     } else if (warp < kWarpMma) {
         // ===== epilogue warps =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
-        if (warp < kWarpEpi1) epilogue_role<NM, 0, OutT>(a, trace, trace_first_arg, &bars, &queue, &info, ab, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
-        else epilogue_role<NM, 1, OutT>(a, trace, trace_first_arg, &bars, &queue, &info, ab, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        if (warp < kWarpEpi1) epilogue_role<NM, 0, OutT>(a, trace, trace_first_arg, &bars, &info, ab, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        else epilogue_role<NM, 1, OutT>(a, trace, trace_first_arg, &bars, &info, ab, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == kWarpMma) {
@@ -1081,9 +980,6 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 }
                 a_parity ^= 1u;
             }
-        } else if (warp >= kWarpNorm && warp < kWarpNorm + 2 && a.fused_norm && static_cast<int64_t>(blockIdx.x) < total_tiles) {
-            // ===== normaliser warps =====
-            normaliser_role<NM, OutT>(a, &queue, ab.flag, warp - kWarpNorm, lane, tiles_per_clip);
         }
         __syncwarp();
     }
@@ -1187,45 +1083,70 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
 }
 
 
-// Clamp pass of the tcgen05 variant for the calls its kernel does not normalise itself (one max over a whole
-// multi-utterance call, audio.py:155; utterances of more than kTcMaxFusedNormTiles tiles): out = max(out, floor) on the
-// already rescaled values, floor = ((g - 8) + 4) / 4 - identical to (max(lg, g - 8) + 4) / 4, and, rounding being
-// monotone, also in half precision.
-template <typename OutT>
-__global__ void __launch_bounds__(256) tc_clamp_kernel(OutT* __restrict__ out, const uint32_t* __restrict__ max_keys, int64_t batch,
-                                                         int64_t elems_per_clip, int global_max) {
-    const int64_t total = batch * elems_per_clip;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    const bool vec = (elems_per_clip & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & (4 * sizeof(OutT) - 1)) == 0;
-    if (vec) {
-        for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < total; i += 4 * stride) {
-            const float g = max_key_decode(__ldg(max_keys + (global_max ? 0 : i / elems_per_clip)));
-            const float floor_y = ((g - 8.0f) + 4.0f) * 0.25f;
-            out_store4(out + i, normalise4(out_load4(out + i), floor_y));
+// ---- finish kernel: what the clamp at max - 8 (audio.py:155) does to each tile ------------------------------------
+// The front-end kernel leaves y = (log10 + 4) / 4 and the extremes of every utterance and of every 128-frame tile; the
+// clamp needs the utterance's (or, for the reference's 2-D semantics, the whole call's) final max g: out = max(y, floor),
+// floor = ((g - 8) + 4) / 4 - identical to (max(lg, g - 8) + 4) / 4, and, rounding being monotone, also in half precision.
+// One warp per tile, a few words per tile: most tiles need nothing (their smallest value is not below g - 8); a tile that
+// lies wholly below the clamp - or was never stored because its samples were all zero - is filled with the constant; the
+// rest (an utterance's tile where the sound stops) is clamped value by value while it is still in L2.
+template <int NM, typename OutT>
+__global__ void __launch_bounds__(256) tc_finish_kernel(const LogmelArgs a, int tiles_per_clip) {
+    const int lane = threadIdx.x & 31;
+    const int64_t total_tiles = a.batch * tiles_per_clip;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+    for (int64_t tile = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < total_tiles; tile += stride) {
+        const int64_t clip = tile / tiles_per_clip;
+        const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kTcTileFrames;
+        const uint32_t gkey = __ldg(a.max_keys + (a.global_max ? 0 : clip));
+        const float g = gkey == 0u ? -10.0f : max_key_decode(gkey);     // (key 0: nothing but silent tiles)
+        const float floor_lg = g - 8.0f;
+        const float floor_y = ((g - 8.0f) + 4.0f) * 0.25f;
+        int action = 0;                      // 0: leave the tile alone, 1: clamp it in place, 2: fill it
+        float fill_value = floor_y;
+        if (a.tile_keys != nullptr) {
+            const uint32_t kmax = __ldg(a.tile_keys + 2 * tile), kmin = __ldg(a.tile_keys + 2 * tile + 1);
+            if (kmax == 0u) {                // never stored: all its samples were zero, every value is log10(1e-10) = -10
+                action = 2;
+                fill_value = floor_lg > -10.0f ? floor_y : (floor_lg != floor_lg ? floor_y : -1.5f);
+            } else {
+                const float tile_max = max_key_decode(kmax), tile_min = max_key_decode(~kmin);
+                if (!(tile_min >= floor_lg)) action = tile_max < floor_lg ? 2 : 1;
+            }
+        } else {
+            const float smallest = max_key_decode(~__ldg(a.min_keys + clip));
+            if (!(smallest >= floor_lg)) action = 1;
         }
-    } else {
-        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-            const float g = max_key_decode(__ldg(max_keys + (global_max ? 0 : i / elems_per_clip)));
-            out_store(out + i, clamp_scaled(out_load(out + i), ((g - 8.0f) + 4.0f) * 0.25f));
-        }
+        if (action == 0) continue;
+        const int frames = a.n_frames - t0 < kTcTileFrames ? a.n_frames - t0 : kTcTileFrames;
+        OutT* tile_out = reinterpret_cast<OutT*>(a.out) + clip * NM * static_cast<int64_t>(a.n_frames) + t0;
+        if (action == 2) fill_tile_tc<NM, OutT>(tile_out, a.n_frames, frames, fill_value, lane);
+        else normalise_tile_tc<NM, OutT>(tile_out, a.n_frames, frames, floor_y, lane);
     }
 }
 
 }  // namespace
 
-cudaError_t launch_tc_clamp(void* out, int out_f16, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip, int global_max,
-                            cudaStream_t stream) {
-    const int64_t total = batch * elems_per_clip;
-    if (total <= 0) return cudaSuccess;
+cudaError_t launch_tc_finish(const LogmelArgs& a, cudaStream_t stream) {
+    const int tiles_per_clip = (a.n_frames + kTcTileFrames - 1) / kTcTileFrames;
+    const int64_t tiles = a.batch * tiles_per_clip;
+    if (tiles <= 0) return cudaSuccess;
     int device = 0, sms = 0;
     cudaError_t err = cudaGetDevice(&device);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (err != cudaSuccess) return err;
-    const int64_t want = (total / 4 + 255) / 256;
-    const unsigned grid = static_cast<unsigned>(want < 8 * static_cast<int64_t>(sms) ? (want > 0 ? want : 1) : 8 * static_cast<int64_t>(sms));
+    const int64_t want = (tiles + 7) / 8;
+    const unsigned grid = static_cast<unsigned>(want < 8 * static_cast<int64_t>(sms) ? want : 8 * static_cast<int64_t>(sms));
     ProfileScope profile(1, stream);
-    if (out_f16) tc_clamp_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<__half*>(out), max_keys, batch, elems_per_clip, global_max);
-    else tc_clamp_kernel<float><<<grid, 256, 0, stream>>>(static_cast<float*>(out), max_keys, batch, elems_per_clip, global_max);
+    if (a.n_mels == 80) {
+        if (a.out_f16) tc_finish_kernel<80, __half><<<grid, 256, 0, stream>>>(a, tiles_per_clip);
+        else tc_finish_kernel<80, float><<<grid, 256, 0, stream>>>(a, tiles_per_clip);
+    } else if (a.n_mels == 128) {
+        if (a.out_f16) tc_finish_kernel<128, __half><<<grid, 256, 0, stream>>>(a, tiles_per_clip);
+        else tc_finish_kernel<128, float><<<grid, 256, 0, stream>>>(a, tiles_per_clip);
+    } else {
+        return cudaErrorInvalidValue;
+    }
     count_launch();
     return cudaGetLastError();
 }

@@ -24,6 +24,23 @@ def test_shards_tile_the_batch_in_rank_order():
         shard_range(10, 2, 2)
 
 
+def test_config5_chunks_cover_every_clip_once():
+    """bench.py --gpus N: rank r walks its shard of the 65,536 clips in 256-clip chunks with globally unique chunk indices."""
+    import bench
+
+    for world in (2, 4, 8):
+        seen = []
+        for rank in range(world):
+            chunks = bench.shard_chunks(bench.TOTAL_CLIPS_CONFIG5, rank, world, 256)
+            assert len(chunks) == bench.TOTAL_CLIPS_CONFIG5 // world // 256
+            assert chunks[0][1] == shard_range(bench.TOTAL_CLIPS_CONFIG5, rank, world)[0]
+            seen += [(g, first, n) for g, first, n in chunks]
+        assert [g for g, _f, _n in seen] == list(range(256))
+        assert sum(n for _g, _f, n in seen) == bench.TOTAL_CLIPS_CONFIG5
+    odd = [c for r in range(3) for c in bench.shard_chunks(1000, r, 3, 256)]
+    assert sum(n for _g, _f, n in odd) == 1000
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

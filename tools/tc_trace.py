@@ -11,6 +11,11 @@ n_mels = int(os.environ.get("N_MELS", "80"))
 B = int(os.environ.get("CLIPS", "256"))
 x = [(0.1 * torch.randn(B, 480000, device="cuda")) for _ in range(1 if os.environ.get("SAME") else 2)]
 x = x * 2
+if os.environ.get("ZEROPAD"):   # config 4: 1-30 s clips zero-padded to 30 s
+    import numpy as np
+    lens = torch.from_numpy(np.random.default_rng(4321).integers(16000, 480001, size=B)).cuda()
+    for v in x:
+        v.masked_fill_(torch.arange(480000, device="cuda")[None, :] >= lens[:, None], 0.0)
 if os.environ.get("PCM"):
     x = [(v * 32768).round().clamp(-32768, 32767).to(torch.int16) for v in x]
 for i in range(3):
