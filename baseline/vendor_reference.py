@@ -6,7 +6,10 @@
 Copies whisper/audio.py, whisper/utils.py and whisper/assets/mel_filters.npz byte for byte into
 baseline/_ref/refwhisper/ next to an empty __init__.py, so `bench.py --impl reference` and the `cpu_baseline`
 leg can time the reference's own `log_mel_spectrogram` (whisper/audio.py:110-157) where /root/reference does not
-exist.  Nothing here enters the git history, and no product code imports it.
+exist; and the reference's two Python packages (whisper/, speech_disorder/), unmodified, into baseline/_ref/tree/ so
+that tests/test_consumers.py can run the REAL consumers of the path - MultiTaskSpeechDataset + collate_fn
+(speech_disorder/dataset.py) and transcribe() (whisper/transcribe.py) - on the GPU box as well.  Nothing here enters the
+git history, and no product code imports it.
 """
 from __future__ import annotations
 
@@ -37,7 +40,22 @@ def vendor(reference: str = "/root/reference") -> bool:
         f.write('"""Package shell around the vendored, unmodified reference files (see baseline/vendor_reference.py)."""\n')
     with open(os.path.join(DEST, "MANIFEST.json"), "w") as f:
         json.dump({"source": src_root, "sha256": manifest}, f, indent=1)
+    tree = os.path.join(HERE, "_ref", "tree")
+    for package in ("whisper", "speech_disorder"):
+        dst = os.path.join(tree, package)
+        if os.path.isdir(dst):
+            shutil.rmtree(dst)
+        shutil.copytree(os.path.join(reference, package), dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
     return True
+
+
+def tree_path():
+    """Directory to put on sys.path to import the reference's `whisper` and `speech_disorder` packages: the reference
+    checkout itself where it exists, else the vendored copy, else None."""
+    if os.path.isdir("/root/reference/whisper"):
+        return "/root/reference"
+    tree = os.path.join(HERE, "_ref", "tree")
+    return tree if os.path.isdir(os.path.join(tree, "whisper")) else None
 
 
 def load():
