@@ -3,7 +3,7 @@
 // reference: whisper/audio.py:145-156).  DESIGN.md section 4.1 has the picture; in short:
 //
 // One persistent CTA per SM, 20 warps, warp-specialised, no __syncthreads in the steady state (mbarriers only):
-//   4 + 4 fold warps: one thread per frame (= TMEM lane), two warps per lane quadrant that split every sweep between
+//   3 x 4 fold warps: one thread per frame (= TMEM lane), three warps per lane quadrant that split every sweep between
 //                     them.  The tile's 130 rows of 160 samples come as TWO half tiles of 66 rows (frames 0-63 / 64-127),
 //                     each ONE TMA tensor copy into its own buffer at pitch 164 words (a 4-D tensor map whose rows overlap,
 //                     see "loaders"): the last of a half's four warps to finish reading it issues the copy of the next
@@ -21,8 +21,9 @@
 //                     tcgen05.mma.kind::f16 (M 128, N 104, K 16; A from TMEM, B = the constant matrix from
 //                     shared memory, fp32 accumulator in TMEM): lo Bh + hi Bl first, hi Bh last, then
 //                     tcgen05.commit -> mbarrier hands the accumulator to the epilogue;
-//   4 + 4 epilogue  : two warps per TMEM lane quadrant pull their half of the 104 accumulator columns
-//     warps           into registers at once (tcgen05.ld), release the accumulator, and add w d^2 to the mels
+//   4 epilogue      : one warp per TMEM lane quadrant (a thread = a frame with ALL its mels in registers - the four warps
+//     warps           run the same code, which is what the instruction cache wants) pulls the 104 accumulator columns
+//                     into registers (tcgen05.ld), releases the accumulator, and adds w d^2 to the mels
 //                     of each bin - mel structure and weights are compile-time constants (FFMA immediates),
 //                     partial sums in registers; after the 4th unit: 2^-2k, log10(max(., 1e-10)), (x + 4) / 4, 128-byte
 //                     coalesced row stores, the utterance's and the tile's extremes (warp REDUX + atomicMax).
@@ -49,7 +50,8 @@ namespace b200mel {
 
 namespace {
 
-constexpr int kWarpO = 4, kWarpEpi0 = 8, kWarpEpi1 = 12, kWarpMma = 16;   // (warps 17-19 complete the warpgroup and idle)
+constexpr int kFoldParts = 3;                 // fold warps per lane quadrant
+constexpr int kWarpEpi0 = 4 * kFoldParts, kWarpMma = kWarpEpi0 + 4;   // fold 0-11, epilogue 12-15, MMA 16 (17-19 complete the warpgroup and idle)
 constexpr int kTcWarps = 20;
 constexpr int kTcThreads = kTcWarps * 32;   // 640
 constexpr uint32_t kSpinLimit = 1u << 17;    // x 20 us hint = 2.6 s: a protocol bug ends the kernel instead of hanging the device
@@ -227,8 +229,7 @@ __constant__ TcUnitIssue c_unit_issue[kTcUnits] = {tc_make_unit_issue().u[0], tc
 // ---- shared memory carve-up ----------------------------------------------------------------------
 constexpr int kSmemOperands = 0;                                                  // 139776 B, 128-byte aligned
 constexpr int kSmemAudio = kTcOperandBytes;                                       // two half tiles: 66 rows x 656 B each
-constexpr int kSmemStraddle = kSmemAudio + kTcHalfStride + kTcHalfBytes;          // [2 buffers][4 quadrants][3][32] floats
-constexpr int kSmemBytes = kSmemStraddle + 2 * 4 * 3 * 32 * 4;
+constexpr int kSmemBytes = kSmemAudio + kTcHalfStride + kTcHalfBytes;
 static_assert(kSmemAudio % 128 == 0 && kTcHalfStride % 128 == 0 && kSmemBytes + 1024 <= 227 * 1024, "shared memory budget");
 
 struct TcBarriers {
@@ -239,7 +240,7 @@ struct TcBarriers {
 
 // what the folds tell the epilogue about a tile: the scale step of each lane quadrant and whether all its samples are
 // zero, [tile parity][quadrant]
-struct TcTileInfo { uint32_t scale[2][4]; uint32_t silent[2][4]; uint32_t quad_max[4][2]; uint32_t released[2]; };
+struct TcTileInfo { uint32_t scale[2][4]; uint32_t silent[2][4]; uint32_t quad_max[4][4]; uint32_t released[2]; };
 
 // ---- normaliser -------------------------------------------------------------------------------------
 // clamp of an already rescaled value y = (lg + 4) / 4 at floor_y = ((g - 8) + 4) / 4 (NaN when the max is NaN, as in
@@ -358,7 +359,7 @@ struct TileCursor {
 //   cooperative mode (`lengths` cuts, unaligned rows, int16 at a clip's ends): the half's 128 fold threads, which would
 //     idle until the rows are there anyway, move them as 16-byte cp.async chunks / converted samples.
 // The copies complete on the half's `full` barrier by byte count; whoever issued them is its one arrival.
-constexpr int kHalfThreads = 128;
+constexpr int kHalfThreads = 2 * kFoldParts * 32;                // the fold threads of a half tile: 192
 constexpr int kChunksPerRow = kHop / 4;                       // 40
 constexpr int kHalfChunks = kTcHalfRows * kChunksPerRow;      // 2640
 constexpr uint32_t kTmaHalfBytes = kTcHalfBytes;              // the whole box, pad words included
@@ -410,13 +411,13 @@ __device__ __forceinline__ bool half_needs_patch(int tma_rows, const TileCoord& 
     const int c2_first = tc.t0 - kTmaLeadRows + kTcHalfFrames * h;
     return c2_first < 0 || c2_first + kTcHalfRows > tma_rows;     // (a superset test; the row test decides)
 }
-// The half's 128 fold threads rewrite the zero-filled rows of half h that hold real or reflected samples: thread pt takes
-// samples pt and pt + 128 of every such row.  In two steps, so that the samples travel while the tensor copy is still in
+// The half's fold threads rewrite the zero-filled rows of half h that hold real or reflected samples: thread pt takes
+// sample pt of every such row (pt < 160).  In two steps, so that the samples travel while the tensor copy is still in
 // flight: patch_fetch (before waiting for the copy) -> registers, patch_store (after it has landed) -> shared memory.
 // Candidates (tile rows): the rows before tensor row 0 (at most two, in a clip's first tile) and the rows from the first
 // tensor row past the end up to the end of the reflected tail (at most three).
 constexpr int kPatchCand = kTmaLeadRows + 4;
-struct PatchRows { float v[kPatchCand][2]; int row[kPatchCand]; };
+struct PatchRows { float v[kPatchCand]; int row[kPatchCand]; };
 __device__ __forceinline__ void patch_fetch(const LogmelArgs& a, int tma_rows, const TileCoord& tc, int h, int pt, PatchRows& p) {
     const float* __restrict__ src = static_cast<const float*>(a.audio) + tc.clip * a.stride_b;
     const int c2_first = tc.t0 - kTmaLeadRows;
@@ -427,26 +428,18 @@ __device__ __forceinline__ void patch_fetch(const LogmelArgs& a, int tma_rows, c
         const int rl = r - kTcHalfFrames * h;                                   // row inside the half
         const bool twice = i >= kTmaLeadRows && r < kTmaLeadRows && c2_first < 0 && r + c2_first < 0;   // (no row twice)
         p.row[i] = (!twice && rl >= 0 && rl < kTcHalfRows && tile_row_needs_patch(a, tma_rows, tc, r)) ? rl : -1;
-        p.v[i][0] = p.v[i][1] = 0.f;
-        if (p.row[i] >= 0) {
-            const int64_t p0 = static_cast<int64_t>(tc.t0 + r) * kHop - kHalfWin;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int64_t pos = p0 + pt + 128 * k;
-                const int64_t idx = reflect_source_index(pos, a.total);
-                if (pt + 128 * k < kHop && pos < a.total + kHalfWin && idx >= 0 && idx < a.n_samples) p.v[i][k] = __ldg(src + idx);
-            }
+        p.v[i] = 0.f;
+        if (p.row[i] >= 0 && pt < kHop) {
+            const int64_t pos = static_cast<int64_t>(tc.t0 + r) * kHop - kHalfWin + pt;
+            const int64_t idx = reflect_source_index(pos, a.total);
+            if (pos < a.total + kHalfWin && idx >= 0 && idx < a.n_samples) p.v[i] = __ldg(src + idx);
         }
     }
 }
 __device__ __forceinline__ void patch_store(const PatchRows& p, float* s_half, int pt) {
 #pragma unroll
     for (int i = 0; i < kPatchCand; ++i)
-        if (p.row[i] >= 0) {
-            float* dst = s_half + p.row[i] * kTcRowPitch;
-            dst[pt] = p.v[i][0];
-            if (pt + 128 < kHop) dst[pt + 128] = p.v[i][1];
-        }
+        if (p.row[i] >= 0 && pt < kHop) s_half[p.row[i] * kTcRowPitch + pt] = p.v[i];
 }
 
 __device__ __forceinline__ void tma_load_half(const CUtensorMap* map, const TileCoord& tc, int h, float* s_half, uint64_t* full) {
@@ -481,12 +474,12 @@ __device__ __forceinline__ void prefetch_half_l2(const LogmelArgs& a, const Tile
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(begin), "r"(static_cast<uint32_t>(end - begin)) : "memory");
 }
 
-// PCM mode, the half's 128 fold threads: int16 samples at the top of the buffer -> float32 rows over the whole buffer.
-// Every thread pulls its chunks of 8 samples into registers; only when all 128 have (named barrier) may the rows be
+// PCM mode, the half's fold threads: int16 samples at the top of the buffer -> float32 rows over the whole buffer.
+// Every thread pulls its chunks of 8 samples into registers; only when all of them have (named barrier) may the rows be
 // written, because they overwrite the staged samples.
 __device__ __forceinline__ void expand_pcm_half(float* s_half, int pt, int bar_id) {
     constexpr int kChunks = kHalfSamples / 8;                                 // 1320 chunks of 8 samples, 20 per row
-    constexpr int kPerThread = (kChunks + kHalfThreads - 1) / kHalfThreads;  // 11
+    constexpr int kPerThread = (kChunks + kHalfThreads - 1) / kHalfThreads;  // 7
     const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(s_half) + kPcmStageOffset);
     uint4 raw[kPerThread];
 #pragma unroll
@@ -494,7 +487,7 @@ __device__ __forceinline__ void expand_pcm_half(float* s_half, int pt, int bar_i
         const int c = pt + i * kHalfThreads;
         raw[i] = c < kChunks ? src[c] : make_uint4(0u, 0u, 0u, 0u);
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");
 #pragma unroll
     for (int i = 0; i < kPerThread; ++i) {
         const int c = pt + i * kHalfThreads;
@@ -512,22 +505,22 @@ __device__ __forceinline__ void expand_pcm_half(float* s_half, int pt, int bar_i
             dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // every row is written before anybody folds
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");   // every row is written before anybody folds
 }
 
-// cooperative mode, the half's 128 fold threads
+// cooperative mode, the half's fold threads
 template <typename InT>
 __device__ __forceinline__ void produce_half(const LogmelArgs& a, const TileCoord& tc, int h, float* s_half, int pt, int bar_id) {
     const InT* __restrict__ row = static_cast<const InT*>(a.audio) + tc.clip * a.stride_b;
     const int64_t valid = valid_samples(a, tc.clip);
     const int64_t s0 = static_cast<int64_t>(tc.t0 + kTcHalfFrames * h) * kHop - kHalfWin;
     const bool aligned = sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // all four warps are done reading the previous tile's rows
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");   // all four warps are done reading the previous tile's rows
     if (s0 >= valid && valid + kHalfWin < a.total) {
         // the whole half lies in the zero tail (`lengths`, right padding) and no reflection reaches a real sample
         float4* z = reinterpret_cast<float4*>(s_half);
         for (int i = pt; i < kTcHalfWords / 4; i += kHalfThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");
         return;
     }
     // chunk c = 40 r + k covers samples s0 + 4c .. + 3 and lands at word 164 r + 4 k
@@ -548,11 +541,11 @@ __device__ __forceinline__ void produce_half(const LogmelArgs& a, const TileCoor
                 dst[i] = v;
             }
         }
-        r += 3; k += 8;                                    // 128 = 3 x 40 + 8
+        r += kHalfThreads / kChunksPerRow; k += kHalfThreads % kChunksPerRow;   // 192 = 4 x 40 + 32
         if (k >= kChunksPerRow) { k -= kChunksPerRow; ++r; }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // every row is written before anybody folds
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");   // every row is written before anybody folds
 }
 
 // ---- fold warps ----------------------------------------------------------------------------------------
@@ -626,23 +619,21 @@ __device__ __forceinline__ float sweep_store(int sweep, uint32_t scale, int j0, 
     }
     return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
 }
-constexpr int kFoldSplit = 7;   // chunks [0, 7) and [7, 13)
 static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) == 96 && tc_hi_col(3) - tc_hi_col(2) == 96 &&
               tc_left_col(1) - tc_left_col(0) == 6 && tc_left_col(3) - tc_left_col(2) == 6, "column arithmetic of sweep_store");
 
 // ---- epilogue ---------------------------------------------------------------------------------------
-template <int NM, int HALF, typename OutT>
+template <int NM, typename OutT>
 __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* trace, const int trace_first_arg, TcBarriers* bars,
-                                              const TcTileInfo* info, TcAbort ab, float* s_straddle,
+                                              const TcTileInfo* info, TcAbort ab,
                                               uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
     using L = TcEpilogueLayout<NM>;
-    constexpr int ACC = L::acc_size(HALF);
     [[maybe_unused]] const int trace_first = trace_first_arg & 0xff;
-    float acc[ACC];
+    float acc[NM];
 #pragma unroll
-    for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
-    const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol + L::col0(HALF);
-    uint32_t d_parity = 0, buf = 0;
+    for (int i = 0; i < NM; ++i) acc[i] = 0.f;
+    const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol;
+    uint32_t d_parity = 0;
     const int64_t my_tiles = static_cast<int64_t>(blockIdx.x) < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TileCoord prev{0, 0};
     TileCursor cursor(tiles_per_clip);
@@ -658,53 +649,48 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
         bool silent = false;
 #pragma unroll 1
         for (int u = 0; u < kTcUnits; ++u) {
-            float d[L::cols(HALF)];
-            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u);
+            if (quad == 0) TC_TRACE(4, ti, 3 * u);
             mbar_wait(&bars->d_full, d_parity, ab);
             d_parity ^= 1u;
             tc_fence_after();
-            tmem_ld_cols<L::cols(HALF)>(d_addr, d);
-            // the quadrant's scale step was written before the folds released the E operand, i.e. before this unit's MMAs
             if (u == 0) {
+                // the quadrant's scale step was written before the folds released the E operand, i.e. before this unit's MMAs
                 unscale = c_fold.unscale[*reinterpret_cast<const volatile uint32_t*>(&info->scale[k & 1][quad])];
                 // a tile whose samples are ALL zero (zero padding) is not stored: the finish kernel fills it (it needs per-tile keys for that)
                 const volatile uint32_t* z = info->silent[k & 1];
                 silent = a.tile_keys != nullptr && (z[0] & z[1] & z[2] & z[3]) != 0u;
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->d_empty);   // the accumulator is in registers: the next unit may overwrite it
-            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 1);
-            // Re and Im of a bin take the same weights: units 0 / 2 (even bins) share one body, units 1 / 3 (odd bins) the other
-            if ((u & 1) == 0) tc_epilogue_unit<NM, 0, HALF>(d, acc);
-            else tc_epilogue_unit<NM, 1, HALF>(d, acc);
-            if (quad == 0) TC_TRACE(4 + HALF, ti, 3 * u + 2);
+            // Re and Im of a bin take the same weights: units 0 / 2 (even bins) share one body, units 1 / 3 (odd bins) the other.
+            // The columns come in L::pieces pieces; the accumulator is released once the last piece is in registers.
+#pragma unroll
+            for (int piece = 0; piece < L::pieces; ++piece) {
+                float d[L::piece_cols];
+                tmem_ld_cols<L::piece_cols>(d_addr + piece * L::piece_cols, d);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (piece == L::pieces - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->d_empty);   // the next unit may overwrite the accumulator
+                    if (quad == 0) TC_TRACE(4, ti, 3 * u + 1);
+                }
+                if ((u & 1) == 0) {
+                    if (piece == 0) tc_epilogue_unit<NM, 0, 0, L::piece_cols>(d, acc);
+                    else tc_epilogue_unit<NM, 0, (L::pieces - 1) * L::piece_cols, L::piece_cols>(d, acc);
+                } else {
+                    if (piece == 0) tc_epilogue_unit<NM, 1, 0, L::piece_cols>(d, acc);
+                    else tc_epilogue_unit<NM, 1, (L::pieces - 1) * L::piece_cols, L::piece_cols>(d, acc);
+                }
+            }
+            if (quad == 0) TC_TRACE(4, ti, 3 * u + 2);
             if (u == kTcUnits - 1) {
-                // ---- finish this tile ----
-                if (quad == 0) TC_TRACE(4 + HALF, ti, 13);
-                // join the mels that straddle the split: half 1 hands its partial sums to half 0
-                float* strad = s_straddle + ((buf * 4 + quad) * 3) * 32 + lane;
-                if constexpr (HALF == 1) {
-#pragma unroll
-                    for (int j = 0; j < L::straddle; ++j) strad[j * 32] = acc[j];
-                }
-                if constexpr (L::straddle > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                if constexpr (HALF == 0) {
-#pragma unroll
-                    for (int j = 0; j < L::straddle; ++j) acc[L::high_base + j] += strad[j * 32];
-                }
-                buf ^= 1u;
-                if (quad == 0) TC_TRACE(4 + HALF, ti, 14);
-                // log10 clamp, coalesced row stores (lane = frame), utterance extremes
+                // ---- finish this tile: log10 clamp, coalesced row stores (lane = frame), extremes ----
                 const int f = quad * 32 + lane, t = prev.t0 + f;
                 const bool live = t < a.n_frames && !silent;
-                constexpr int m_begin = HALF == 0 ? 0 : L::low_mels, m_end = HALF == 0 ? L::low_mels : NM;
                 const int64_t pitch = a.n_frames;
-                OutT* const out = reinterpret_cast<OutT*>(a.out) + (prev.clip * NM + m_begin) * pitch + t;
+                OutT* const out = reinterpret_cast<OutT*>(a.out) + prev.clip * NM * pitch + t;
                 // The affine half of the normalisation, (x + 4) / 4, is applied here (one FFMA, the same single rounding as
-                // audio.py:156); only the clamp at max - 8 is left - for the normaliser warps, which skip the utterance when
-                // its smallest value is not below max - 8 (tracked here as well), or for the clamp pass (launch_tc_clamp).
+                // audio.py:156); only the clamp at max - 8 is left for the finish kernel - which skips the tile when its
+                // smallest value is not below max - 8 (tracked here as well).
                 float mx = __uint_as_float(0xff800000u), mn = __uint_as_float(0x7f800000u);
                 if (live) {
                     constexpr float scale = 0.25f, shift = 1.0f;
@@ -714,27 +700,20 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
                     constexpr float kLog10Of2 = 0.30102999566398120f;
                     const float2 scale2 = make_float2(scale, scale), shift2 = make_float2(shift, shift), unscale2 = make_float2(unscale, unscale);
 #pragma unroll
-                    for (int m = m_begin; m + 1 < m_end; m += 2) {
-                        const float2 s = __fmul2_rn(make_float2(acc[m - L::acc_base(HALF)], acc[m + 1 - L::acc_base(HALF)]), unscale2);
+                    for (int m = 0; m < NM; m += 2) {
+                        const float2 s = __fmul2_rn(make_float2(acc[m], acc[m + 1]), unscale2);
                         const float2 l2 = make_float2(log2_clamped(s.x), log2_clamped(s.y));
                         const float2 lg = __fmul2_rn(l2, make_float2(kLog10Of2, kLog10Of2));
                         const float2 y = __ffma2_rn(lg, scale2, shift2);
-                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin), y.x);
-                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1 - m_begin), y.y);
+                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m), y.x);
+                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1), y.y);
                         mx = max_nan(mx, max_nan(lg.x, lg.y));
                         mn = fminf(mn, fminf(lg.x, lg.y));
                     }
-                    if constexpr ((m_end - m_begin) % 2 == 1) {
-                        constexpr int m = m_end - 1;
-                        const float lg = log10_clamped(acc[m - L::acc_base(HALF)] * unscale);
-                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m - m_begin), fmaf(lg, scale, shift));
-                        mx = max_nan(mx, lg);
-                        mn = fminf(mn, lg);
-                    }
                 }
 #pragma unroll
-                for (int i = 0; i < ACC; ++i) acc[i] = 0.f;
-                if (quad == 0) TC_TRACE(4 + HALF, ti, 15);
+                for (int i = 0; i < NM; ++i) acc[i] = 0.f;
+                if (quad == 0) TC_TRACE(4, ti, 15);
                 uint32_t key = live ? max_key_encode(mx) : 0u;
                 key = __reduce_max_sync(0xffffffffu, key);
                 uint32_t inv = live ? ~max_key_encode(mn) : 0u;
@@ -748,7 +727,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
                         atomicMax(tk + 1, inv);
                     }
                 }
-                if (quad == 0) TC_TRACE(4 + HALF, ti, 12);
+                if (quad == 0) TC_TRACE(4, ti, 12);
             }
         }
     }
@@ -761,7 +740,6 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     const int trace_first = trace_first_arg & 0xff;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_audio = reinterpret_cast<float*>(smem_raw + kSmemAudio);
-    float* s_straddle = reinterpret_cast<float*>(smem_raw + kSmemStraddle);
     __shared__ __align__(8) TcBarriers bars;
     __shared__ TcTileInfo info;
     __shared__ uint32_t s_tmem, s_abort;
@@ -781,10 +759,10 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     if (tid == 32) {
         mbar_init(&bars.audio_full[0], 1); mbar_init(&bars.audio_full[1], 1);
         info.released[0] = info.released[1] = 0;
-        mbar_init(&bars.a_full[0], 8); mbar_init(&bars.a_full[1], 8);
+        mbar_init(&bars.a_full[0], 4 * kFoldParts); mbar_init(&bars.a_full[1], 4 * kFoldParts);
         mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
         mbar_init(&bars.d_full, 1);
-        mbar_init(&bars.d_empty, 8);
+        mbar_init(&bars.d_empty, 4);
         s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -803,7 +781,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     const uint32_t tmem = s_tmem;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);   // this warp's TMEM lane quadrant
 
-    if (warp < kWarpO) {
+    if (warp < 4) {
         // zero every column once (every operand column is rewritten each tile; this only keeps idle lanes finite)
         for (int c = 0; c < 512; c += 4) { const uint32_t z[4] = {0u, 0u, 0u, 0u}; tmem_st4(lane_addr + c, z); }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -813,14 +791,14 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     tc_fence_after();
 
     // register budget per warpgroup: the CTA is launched with 5 x 96; the warpgroups trade inside that total
-    // (a setmaxnreg.inc can only take what another warpgroup released): folds 80 + 80, epilogue 144 + 144, rest 32
+    // (a setmaxnreg.inc can only take what another warpgroup released): folds 3 x 72, epilogue 232, rest 32
     if (warp < kWarpEpi0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ===== fold warps: two per lane quadrant; both do half of the E sweep, then half of the O sweep =====
-        const int part = warp < kWarpO ? 0 : 1;
+        const int part = warp >> 2;                                           // 0..2
         const int half = quad >> 1;
         float* s_half = s_audio + half * (kTcHalfStride / 4);
-        const int half_thread = (quad & 1) * 32 + lane + 64 * part;          // 0..127 among the half's fold threads
+        const int half_thread = (quad & 1) * 32 + lane + 64 * part;          // 0..191 among the half's fold threads
         const uint32_t quad_rows = smem_u32(s_half) + (quad & 1) * 32 * (kTcRowPitch * 4);
         const uint32_t fr = quad_rows + lane * (kTcRowPitch * 4);
         const int half_bar = 9 + half;                                        // named barrier of the half's four warps
@@ -840,12 +818,12 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         uint32_t last_scale = 5u;                                             // (2^12: right for samples of order 1)
         int ti = 0;
         TileCursor cursor(tiles_per_clip);
-        if (part == 0 && (quad & 1) == 0 && lane == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) {
+        if (part == 0 && (quad & 1) == 0 && lane == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) {   // warps 0 and 2
             issue_half(cursor.at);
             if (static_cast<int64_t>(blockIdx.x) + gridDim.x < total_tiles) prefetch_half(cursor.peek_next());
         }
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, cursor.advance()) {
-            if (quad == 0) TC_TRACE(1 + part, ti, 0);
+            if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 0);
             const TileCoord tcl = cursor.at;
             const int mode = half_mode<InT>(a, tma_rows, tcl, half);
             if (mode == kModeTma) {
@@ -856,7 +834,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                         patch_fetch(a, tma_rows, tcl, half, half_thread, rows);
                         mbar_wait(&bars.audio_full[half], full_parity, ab);
                         patch_store(rows, s_half, half_thread);
-                        asm volatile("bar.sync %0, 128;" ::"r"(half_bar) : "memory");
+                        asm volatile("bar.sync %0, %1;" ::"r"(half_bar), "n"(kHalfThreads) : "memory");
                     } else {
                         mbar_wait(&bars.audio_full[half], full_parity, ab);
                     }
@@ -869,26 +847,29 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
             } else {
                 produce_half<InT>(a, tcl, half, s_half, half_thread, half_bar);
             }
-            if (quad == 0) TC_TRACE(1 + part, ti, 1);
+            if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 1);
             uint32_t scale = last_scale;
 #pragma unroll 1
             for (int sweep = 0; sweep < 2; ++sweep) {
                 mbar_wait(&bars.a_empty[sweep], parity ^ 1u, ab);   // the tensor cores are done with the previous tile's operand
-                if (quad == 0) TC_TRACE(1 + part, ti, 2 + 3 * sweep);
+                if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 2 + 3 * sweep);
                 tc_fence_after();
-                // warp `part` takes the first chunks of the E sweep and the last ones of the O sweep (7 + 6 either way)
-                const bool first_half = (part == 0) == (sweep == 0);
-                const int j0 = first_half ? 0 : kFoldSplit, j1 = first_half ? kFoldSplit : kTcChunks;
+                // the quadrant's three warps take 5 + 4 + 4 chunks of a sweep; the O sweep hands the 5 to the other end, so
+                // that the warps come out at 9 / 8 / 9 chunks per tile
+                const int slot = sweep == 0 ? part : kFoldParts - 1 - part;
+                const int j0 = slot == 0 ? 0 : 1 + 4 * slot, j1 = 5 + 4 * slot;
                 if (sweep == 0) {
                     // the E sweep with the previous tile's scale step, tracking the largest |sample|; the quadrant's two warps
                     // then agree on the step this tile calls for and repeat their chunks if it is another one
                     const float m = sweep_store<true>(0, scale, j0, j1, fr, lane_addr);
                     const uint32_t mine = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like their bits
                     if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&info.quad_max[quad][part]) = mine;
-                    asm volatile("bar.sync %0, 64;" ::"r"(5 + quad) : "memory");
-                    // (the partner reads this tile's value before either warp can write the next tile's: the O sweep is between)
-                    const uint32_t other = *reinterpret_cast<volatile uint32_t*>(&info.quad_max[quad][part ^ 1]);
-                    const uint32_t want = static_cast<uint32_t>(tc_scale_index(mine > other ? mine : other));
+                    asm volatile("bar.sync %0, %1;" ::"r"(5 + quad), "n"(32 * kFoldParts) : "memory");
+                    // (the partners read this tile's values before any of them can write the next tile's: the O sweep is between)
+                    const volatile uint32_t* qm = info.quad_max[quad];
+                    uint32_t other = qm[0] > qm[1] ? qm[0] : qm[1];
+                    other = other > qm[2] ? other : qm[2];
+                    const uint32_t want = static_cast<uint32_t>(tc_scale_index(other));
                     if (want != scale && !TC_DEBUG_FLAG(0x4000)) {
                         scale = want;
                         sweep_store<false>(0, scale, j0, j1, fr, lane_addr);
@@ -896,12 +877,12 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                     last_scale = scale;
                     if (part == 0 && lane == 0) {
                         *reinterpret_cast<volatile uint32_t*>(&info.scale[ti & 1][quad]) = scale;
-                        *reinterpret_cast<volatile uint32_t*>(&info.silent[ti & 1][quad]) = (mine | other) == 0u ? 1u : 0u;
+                        *reinterpret_cast<volatile uint32_t*>(&info.silent[ti & 1][quad]) = other == 0u ? 1u : 0u;
                     }
                 } else {
                     sweep_store<false>(1, scale, j0, j1, fr, lane_addr);
                 }
-                if (quad == 0) TC_TRACE(1 + part, ti, 3 + 3 * sweep);
+                if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 3 + 3 * sweep);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -911,7 +892,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                         // this warp has read the half's rows for the last time; the last of the four warps to say so brings the
                         // next tile's rows (and asks L2 for the ones after)
                         __threadfence_block();
-                        if (atomicAdd(&info.released[half], 1u) == 3u) {
+                        if (atomicAdd(&info.released[half], 1u) == 2u * kFoldParts - 1u) {
                             *reinterpret_cast<volatile uint32_t*>(&info.released[half]) = 0u;
                             if (tile + gridDim.x < total_tiles) {
                                 const TileCoord next = cursor.peek_next();
@@ -926,15 +907,14 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                         }
                     }
                 }
-                if (quad == 0) TC_TRACE(1 + part, ti, 4 + 3 * sweep);
+                if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 4 + 3 * sweep);
             }
             parity ^= 1u;
         }
     } else if (warp < kWarpMma) {
         // ===== epilogue warps =====
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
-        if (warp < kWarpEpi1) epilogue_role<NM, 0, OutT>(a, trace, trace_first_arg, &bars, &info, ab, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
-        else epilogue_role<NM, 1, OutT>(a, trace, trace_first_arg, &bars, &info, ab, s_straddle, tmem, quad, lane, total_tiles, tiles_per_clip);
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        epilogue_role<NM, OutT>(a, trace, trace_first_arg, &bars, &info, ab, tmem, quad, lane, total_tiles, tiles_per_clip);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == kWarpMma) {
@@ -1067,7 +1047,7 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
         cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost);
         long long t0 = 0;
         for (int i = 0; i < kTraceRoles * kTraceTiles * kTraceEvents; ++i) { const long long v = host[i]; if (v != 0 && (t0 == 0 || v < t0)) t0 = v; }
-        static const char* names[kTraceRoles] = {"-", "fold-0", "fold-1", "mma", "epi-0", "epi-1"};
+        static const char* names[kTraceRoles] = {"-", "fold-0", "fold-1", "mma", "epi", "fold-2"};
         for (int r = 0; r < kTraceRoles; ++r)
             for (int t = 0; t < kTraceTiles; ++t) {
                 std::fprintf(stderr, "trace %-8s tile %d:", names[r], t + trace_first);

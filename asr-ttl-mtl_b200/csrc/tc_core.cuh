@@ -290,9 +290,8 @@ inline void tc_sweep_chunk_host(const float* fr, const TcFoldOffsets& o, const T
 B200_HD float tc_abs_max(float m, float v) { return fmaxf(m, fabsf(v)); }
 
 // ---- epilogue: mel structure and weights are compile-time constants (mel_bands.h) ---------------------
-// Each bin feeds at most two neighbouring mels.  An epilogue thread owns one frame and one HALF of
-// every unit's columns (k' < split or k' >= split, i.e. bins below / above 2 split) and keeps the mels
-// its bins touch in registers; the (at most 3) mels that straddle the split are joined at the end.
+// Each bin feeds at most two neighbouring mels.  An epilogue thread owns one frame and keeps all its mels in
+// registers; the accumulator columns of a unit arrive in one piece (80 mels) or two (128 mels: registers).
 template <int NM> B200_HD constexpr int tc_bin_mel0(int k) { return MelBands<NM>::bin_mel0[k]; }
 template <int NM> B200_HD constexpr int tc_bin_count(int k) { return MelBands<NM>::bin_count[k]; }
 template <int NM> B200_HD constexpr bool tc_bands_supported() {   // the per-bin view agrees with the band edges
@@ -304,45 +303,23 @@ template <int NM> B200_HD constexpr bool tc_bands_supported() {   // the per-bin
     }
     return true;
 }
+static_assert(tc_bands_supported<80>() && tc_bands_supported<128>(), "every bin must feed at most two neighbouring mels");
 
-template <int NM> B200_HD constexpr int tc_last_low_mel(int split_bin) {    // last mel with a bin below the split
-    int m = -1;
-    for (int i = 0; i < NM; ++i)
-        if (MelBands<NM>::first[i] < split_bin) m = i;
-    return m;
-}
-template <int NM> B200_HD constexpr int tc_first_high_mel(int split_bin) {  // first mel with a bin at or above it
-    for (int i = 0; i < NM; ++i)
-        if (MelBands<NM>::last[i] >= split_bin) return i;
-    return NM;
-}
-
+// how the 104 accumulator columns of a unit are pulled into registers: all at once, or as two pieces
 template <int NM> struct TcEpilogueLayout {
-    static constexpr int split = NM == 80 ? 44 : 40;      // columns [0, split) -> half 0, [split, 104) -> half 1
-    static constexpr int split_bin = 2 * split;           // half 0: bins < split_bin
-    static constexpr int low_mels = tc_last_low_mel<NM>(split_bin) + 1;    // half 0 accumulates mels [0, low_mels)
-    static constexpr int high_base = tc_first_high_mel<NM>(split_bin);     // half 1 accumulates mels [high_base, NM)
-    static constexpr int high_mels = NM - high_base;
-    static constexpr int straddle = low_mels - high_base;                  // mels both halves touch
-    static constexpr int cols(int half) { return half == 0 ? split : kTcN - split; }
-    static constexpr int col0(int half) { return half == 0 ? 0 : split; }
-    static constexpr int acc_size(int half) { return half == 0 ? low_mels : high_mels; }
-    static constexpr int acc_base(int half) { return half == 0 ? 0 : high_base; }
-    static_assert(tc_bands_supported<NM>(), "every bin must feed at most two neighbouring mels");
-    static_assert(straddle >= 0 && straddle <= 3, "unexpected mel layout around the split");
+    static constexpr int pieces = NM == 80 ? 1 : 2;
+    static constexpr int piece_cols = kTcN / pieces;              // 104 or 52
+    static_assert(piece_cols % 4 == 0, "tensor-memory loads come in multiples of 4 columns");
 };
 
 // one accumulator column: t = D[frame][k']^2 of unit U; adds w * t to the (<= 2) mels of its bin
-template <int NM, int U, int HALF, int C, int ACC>
-B200_HD void tc_epilogue_col(float t, float (&acc)[ACC]) {
-    using L = TcEpilogueLayout<NM>;
-    constexpr int kp = L::col0(HALF) + C;
-    if constexpr (kp < kTcBinsPerUnit) {
-        constexpr int bin = tc_unit_bin(U, kp);
+template <int NM, int U, int KP>
+B200_HD void tc_epilogue_col(float t, float (&acc)[NM]) {
+    if constexpr (KP < kTcBinsPerUnit) {
+        constexpr int bin = tc_unit_bin(U, KP);
         constexpr int cnt = tc_bin_count<NM>(bin);
         if constexpr (cnt > 0) {
-            constexpr int m0 = tc_bin_mel0<NM>(bin) - L::acc_base(HALF);
-            static_assert(m0 >= 0 && m0 + cnt <= ACC, "bin outside the half's mel range");
+            constexpr int m0 = tc_bin_mel0<NM>(bin);
             constexpr float w0 = MelBands<NM>::bin_weight[bin][0] * kTcPowerUnscale;   // FFMA immediates
             constexpr float w1 = MelBands<NM>::bin_weight[bin][1] * kTcPowerUnscale;
             acc[m0] = fmaf(w0, t, acc[m0]);
@@ -350,44 +327,42 @@ B200_HD void tc_epilogue_col(float t, float (&acc)[ACC]) {
         }
     }
 }
-template <int NM, int U, int HALF, int C> B200_HD constexpr bool tc_col_used() {
-    constexpr int kp = TcEpilogueLayout<NM>::col0(HALF) + C;
-    if constexpr (kp < kTcBinsPerUnit) return tc_bin_count<NM>(tc_unit_bin(U, kp)) > 0;
+template <int NM, int U, int KP> B200_HD constexpr bool tc_col_used() {
+    if constexpr (KP < kTcBinsPerUnit) return tc_bin_count<NM>(tc_unit_bin(U, KP)) > 0;
     else return false;
 }
 
 // two neighbouring columns: the squares are one packed multiply (FMUL2) on the register pair tcgen05.ld delivered
-template <int NM, int U, int HALF, int P, int ACC, int NCOLS>
-B200_HD void tc_epilogue_pair(const float (&d)[NCOLS], float (&acc)[ACC]) {
+template <int NM, int U, int C0, int P, int NCOLS>
+B200_HD void tc_epilogue_pair(const float (&d)[NCOLS], float (&acc)[NM]) {
     constexpr int C = 2 * P;
-    constexpr bool use_a = tc_col_used<NM, U, HALF, C>(), use_b = tc_col_used<NM, U, HALF, C + 1>();
+    constexpr bool use_a = tc_col_used<NM, U, C0 + C>(), use_b = tc_col_used<NM, U, C0 + C + 1>();
     if constexpr (use_a && use_b) {
 #if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
         const float2 v = make_float2(d[C], d[C + 1]);
         const float2 t = __fmul2_rn(v, v);
-        tc_epilogue_col<NM, U, HALF, C, ACC>(t.x, acc);
-        tc_epilogue_col<NM, U, HALF, C + 1, ACC>(t.y, acc);
+        tc_epilogue_col<NM, U, C0 + C>(t.x, acc);
+        tc_epilogue_col<NM, U, C0 + C + 1>(t.y, acc);
 #else
-        tc_epilogue_col<NM, U, HALF, C, ACC>(d[C] * d[C], acc);
-        tc_epilogue_col<NM, U, HALF, C + 1, ACC>(d[C + 1] * d[C + 1], acc);
+        tc_epilogue_col<NM, U, C0 + C>(d[C] * d[C], acc);
+        tc_epilogue_col<NM, U, C0 + C + 1>(d[C + 1] * d[C + 1], acc);
 #endif
     } else {
-        if constexpr (use_a) tc_epilogue_col<NM, U, HALF, C, ACC>(d[C] * d[C], acc);
-        if constexpr (use_b) tc_epilogue_col<NM, U, HALF, C + 1, ACC>(d[C + 1] * d[C + 1], acc);
+        if constexpr (use_a) tc_epilogue_col<NM, U, C0 + C>(d[C] * d[C], acc);
+        if constexpr (use_b) tc_epilogue_col<NM, U, C0 + C + 1>(d[C + 1] * d[C + 1], acc);
     }
 }
 
-template <int NM, int U, int HALF, int ACC, int NCOLS, int... P>
-B200_HD void tc_epilogue_cols(const float (&d)[NCOLS], float (&acc)[ACC], std::integer_sequence<int, P...>) {
-    (tc_epilogue_pair<NM, U, HALF, P, ACC, NCOLS>(d, acc), ...);
+template <int NM, int U, int C0, int NCOLS, int... P>
+B200_HD void tc_epilogue_cols(const float (&d)[NCOLS], float (&acc)[NM], std::integer_sequence<int, P...>) {
+    (tc_epilogue_pair<NM, U, C0, P, NCOLS>(d, acc), ...);
 }
 
-// all columns of one half of unit U (d[c] = accumulator column col0(HALF) + c)
-template <int NM, int U, int HALF, int ACC, int NCOLS>
-B200_HD void tc_epilogue_unit(const float (&d)[NCOLS], float (&acc)[ACC]) {
-    static_assert(NCOLS == TcEpilogueLayout<NM>::cols(HALF) && ACC == TcEpilogueLayout<NM>::acc_size(HALF), "half shape");
-    static_assert(NCOLS % 2 == 0, "columns are processed in pairs");
-    tc_epilogue_cols<NM, U, HALF, ACC, NCOLS>(d, acc, std::make_integer_sequence<int, NCOLS / 2>{});
+// columns [C0, C0 + NCOLS) of unit U (d[c] = accumulator column C0 + c) into the frame's mel sums
+template <int NM, int U, int C0, int NCOLS>
+B200_HD void tc_epilogue_unit(const float (&d)[NCOLS], float (&acc)[NM]) {
+    static_assert(NCOLS % 2 == 0 && C0 % 2 == 0, "columns are processed in pairs");
+    tc_epilogue_cols<NM, U, C0, NCOLS>(d, acc, std::make_integer_sequence<int, NCOLS / 2>{});
 }
 
 }  // namespace b200mel

@@ -109,21 +109,21 @@ int quadrant_scale(const float* s_audio, int q) {
 }
 
 template <int NM, int U>
-void epilogue_unit(const float* d, float* acc0, float* acc1) {
+void epilogue_unit(const float* d, float (&acc)[NM]) {
     using L = TcEpilogueLayout<NM>;
-    float d0[L::cols(0)], d1[L::cols(1)];
-    float (&a0)[L::acc_size(0)] = *reinterpret_cast<float (*)[L::acc_size(0)]>(acc0);
-    float (&a1)[L::acc_size(1)] = *reinterpret_cast<float (*)[L::acc_size(1)]>(acc1);
-    for (int c = 0; c < L::cols(0); ++c) d0[c] = d[c];
-    for (int c = 0; c < L::cols(1); ++c) d1[c] = d[L::split + c];
-    tc_epilogue_unit<NM, U, 0>(d0, a0);
-    tc_epilogue_unit<NM, U, 1>(d1, a1);
+    // the kernel pulls a unit's columns as L::pieces pieces, in column order
+    float piece[L::piece_cols];
+    for (int c = 0; c < L::piece_cols; ++c) piece[c] = d[c];
+    tc_epilogue_unit<NM, U, 0, L::piece_cols>(piece, acc);
+    if constexpr (L::pieces == 2) {
+        for (int c = 0; c < L::piece_cols; ++c) piece[c] = d[L::piece_cols + c];
+        tc_epilogue_unit<NM, U, L::piece_cols, L::piece_cols>(piece, acc);
+    }
 }
 
 template <int NM>
 int run(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad, const float* filters, float* out,
         int do_normalise) {
-    using L = TcEpilogueLayout<NM>;
     static TcTables tab;
     if (build_tc_tables(NM, filters, &tab) != kTablesOk) return 5;
     const int64_t total = n_samples + (right_pad > 0 ? right_pad : 0);
@@ -157,21 +157,19 @@ int run(const float* audio, int64_t n_samples, int64_t valid, int64_t right_pad,
             sweep_to_tmem(1, scale[f / 32], fr, lane);
         }
         for (int f = 0; f < kTcTileFrames && t0 + f < n_frames; ++f) {
-            float acc0[L::acc_size(0)] = {0.f}, acc1[L::acc_size(1)] = {0.f};
+            float acc[NM] = {0.f};
             for (int u = 0; u < kTcUnits; ++u) {
                 float d[kTcN];
                 for (int kp = 0; kp < kTcN; ++kp) d[kp] = unit_column(tab, tmem, f, u, kp);
                 switch (u) {
-                    case 0: epilogue_unit<NM, 0>(d, acc0, acc1); break;
-                    case 1: epilogue_unit<NM, 1>(d, acc0, acc1); break;
-                    case 2: epilogue_unit<NM, 2>(d, acc0, acc1); break;
-                    default: epilogue_unit<NM, 3>(d, acc0, acc1); break;
+                    case 0: epilogue_unit<NM, 0>(d, acc); break;
+                    case 1: epilogue_unit<NM, 1>(d, acc); break;
+                    case 2: epilogue_unit<NM, 2>(d, acc); break;
+                    default: epilogue_unit<NM, 3>(d, acc); break;
                 }
             }
             for (int m = 0; m < NM; ++m) {
-                float s = 0.f;
-                if (m < L::low_mels) s += acc0[m];
-                if (m >= L::high_base) s += acc1[m - L::high_base];
+                const float s = acc[m];
                 const float lg = log10_clamped(s * kFold.unscale[scale[f / 32]]);
                 out[static_cast<int64_t>(m) * n_frames + t0 + f] = lg;
                 clip_key = std::max(clip_key, max_key_encode(lg));
