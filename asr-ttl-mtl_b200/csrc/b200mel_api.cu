@@ -261,7 +261,9 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int global_max = (flags & B200MEL_FLAG_GLOBAL_MAX) ? 1 : 0;
     uint32_t* keys = static_cast<uint32_t*>(workspace);
-    B200_CUDA(cudaMemsetAsync(keys, 0, workspace_words(batch) * sizeof(uint32_t), stream));
+    const bool tile_keys = (flags & B200MEL_FLAG_TILE_KEYS) && variant == B200MEL_VARIANT_TCGEN05;
+    // one memset for everything the kernels count in: the per-utterance words and, right behind them, the per-tile keys
+    B200_CUDA(cudaMemsetAsync(keys, 0, tile_keys ? b200mel_workspace_bytes_tiles(batch, n_frames) : workspace_words(batch) * sizeof(uint32_t), stream));
 
     const int64_t elems_per_clip = static_cast<int64_t>(plan->n_mels) * n_frames;
     const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
@@ -282,10 +284,7 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     a.tile_counter = keys + 2 * batch;
     a.min_keys = keys + 2 * batch + 1;
     a.tile_keys = nullptr;
-    if ((flags & B200MEL_FLAG_TILE_KEYS) && variant == B200MEL_VARIANT_TCGEN05) {
-        a.tile_keys = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + b200mel_workspace_bytes(batch));
-        B200_CUDA(cudaMemsetAsync(a.tile_keys, 0, static_cast<size_t>(batch) * tc_tiles_per_clip(n_frames) * 2 * sizeof(uint32_t), stream));
-    }
+    if (tile_keys) a.tile_keys = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + b200mel_workspace_bytes(batch));
     a.global_max = global_max;
     // FFT variant: one max per utterance (or a single utterance, where the call's max is the utterance's) is normalised
     // inside the kernel by the CTA that finishes the utterance, unless the utterance is very long; the tcgen05 variant

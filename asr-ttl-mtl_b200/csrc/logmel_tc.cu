@@ -1072,6 +1072,9 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
 // rest (an utterance's tile where the sound stops) is clamped value by value while it is still in L2.
 template <int NM, typename OutT>
 __global__ void __launch_bounds__(256) tc_finish_kernel(const LogmelArgs a, int tiles_per_clip) {
+    // launched with programmatic stream serialisation: the grid is set up while the front-end kernel drains, and waits
+    // here until that kernel has completed and its writes are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int64_t total_tiles = a.batch * tiles_per_clip;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
@@ -1118,15 +1121,26 @@ cudaError_t launch_tc_finish(const LogmelArgs& a, cudaStream_t stream) {
     const int64_t want = (tiles + 7) / 8;
     const unsigned grid = static_cast<unsigned>(want < 8 * static_cast<int64_t>(sms) ? want : 8 * static_cast<int64_t>(sms));
     ProfileScope profile(1, stream);
+    cudaLaunchConfig_t config = {};
+    config.gridDim = dim3(grid);
+    config.blockDim = dim3(256);
+    config.dynamicSmemBytes = 0;
+    config.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    config.attrs = attr;
+    config.numAttrs = 1;
     if (a.n_mels == 80) {
-        if (a.out_f16) tc_finish_kernel<80, __half><<<grid, 256, 0, stream>>>(a, tiles_per_clip);
-        else tc_finish_kernel<80, float><<<grid, 256, 0, stream>>>(a, tiles_per_clip);
+        err = a.out_f16 ? cudaLaunchKernelEx(&config, tc_finish_kernel<80, __half>, a, tiles_per_clip)
+                        : cudaLaunchKernelEx(&config, tc_finish_kernel<80, float>, a, tiles_per_clip);
     } else if (a.n_mels == 128) {
-        if (a.out_f16) tc_finish_kernel<128, __half><<<grid, 256, 0, stream>>>(a, tiles_per_clip);
-        else tc_finish_kernel<128, float><<<grid, 256, 0, stream>>>(a, tiles_per_clip);
+        err = a.out_f16 ? cudaLaunchKernelEx(&config, tc_finish_kernel<128, __half>, a, tiles_per_clip)
+                        : cudaLaunchKernelEx(&config, tc_finish_kernel<128, float>, a, tiles_per_clip);
     } else {
         return cudaErrorInvalidValue;
     }
+    if (err != cudaSuccess) return err;
     count_launch();
     return cudaGetLastError();
 }
