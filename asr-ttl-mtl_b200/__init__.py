@@ -23,3 +23,4 @@ from .audio import (  # noqa: F401
 )
 from .install import install, uninstall  # noqa: F401
 from .sharding import shard_range  # noqa: F401
+from .stem import encoder_stem, log_mel_encoder_stem  # noqa: F401

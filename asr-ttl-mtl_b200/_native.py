@@ -22,6 +22,7 @@ VARIANT_AUTO, VARIANT_FFT, VARIANT_TCGEN05 = 0, 1, 2
 FLAG_GLOBAL_MAX = 1
 FLAG_TILE_KEYS = 2
 FLAG_OUT_F16 = 4
+FLAG_DEFER_CLAMP = 8
 ABI_VERSION = 2
 
 #: every symbol include/b200mel.h declares: (restype, argtypes)
@@ -38,6 +39,8 @@ SYMBOLS = {
     "b200mel_logmel_device": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                       c_void_p, c_void_p, c_uint, c_int, c_void_p]),
     "b200mel_normalise_device": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_uint, c_void_p]),
+    "b200mel_stem_conv1_gelu_device": (c_int, [c_void_p, c_void_p, c_uint, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int,
+                                               c_void_p, c_void_p]),
     "b200mel_logmel_host": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                     c_void_p, c_uint, c_int]),
     "b200mel_launch_count": (c_uint64, []),

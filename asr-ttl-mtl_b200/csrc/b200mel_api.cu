@@ -293,12 +293,30 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     a.n_rows = plan->n_rows;
     a.tables = plan->d_tables;
     if (a.out_f16 && variant != B200MEL_VARIANT_TCGEN05) return B200MEL_ERR_BAD_ARGUMENT;
+    if ((flags & B200MEL_FLAG_DEFER_CLAMP) && (variant != B200MEL_VARIANT_TCGEN05 || a.out_f16)) return B200MEL_ERR_BAD_ARGUMENT;
     if (variant == B200MEL_VARIANT_TCGEN05)
         B200_CUDA(launch_tc_pass1(a, plan->d_tc_tables, dtype, stream));
     else
         B200_CUDA(launch_fft_fused(a, dtype, stream));
-    if (variant == B200MEL_VARIANT_TCGEN05) B200_CUDA(launch_tc_finish(a, stream));
-    else if (!a.fused_norm) B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, global_max, stream));
+    if (variant == B200MEL_VARIANT_TCGEN05) {
+        if (!(flags & B200MEL_FLAG_DEFER_CLAMP)) B200_CUDA(launch_tc_finish(a, stream));
+    } else if (!a.fused_norm) B200_CUDA(launch_normalise(out, keys, batch, elems_per_clip, global_max, stream));
+    return B200MEL_OK;
+}
+
+int b200mel_stem_conv1_gelu_device(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels,
+                                   int64_t n_frames, const float* weight, const float* bias, int n_state, float* out,
+                                   void* stream) {
+    if (mel == nullptr || weight == nullptr || bias == nullptr || out == nullptr) return B200MEL_ERR_NULL_POINTER;
+    if (n_mels != 80) return B200MEL_ERR_BAD_N_MELS;
+    if (batch < 0 || n_frames < 0 || n_frames > 0x7fffffff || n_state <= 0 || n_state % 128 != 0 || n_state > 128 * 148)
+        return B200MEL_ERR_BAD_ARGUMENT;
+    const uint32_t* keys = static_cast<const uint32_t*>(workspace);
+    const uint32_t* tile_keys = nullptr;
+    if (keys != nullptr && (flags & B200MEL_FLAG_TILE_KEYS))
+        tile_keys = reinterpret_cast<const uint32_t*>(static_cast<const char*>(workspace) + b200mel_workspace_bytes(batch));
+    B200_CUDA(launch_stem_conv1_gelu(mel, keys, tile_keys, (flags & B200MEL_FLAG_GLOBAL_MAX) ? 1 : 0, batch, static_cast<int>(n_frames),
+                                     weight, bias, n_state, out, static_cast<cudaStream_t>(stream)));
     return B200MEL_OK;
 }
 

@@ -52,6 +52,11 @@ unsigned tc_kernel_fault(unsigned* cta);
 cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch, int64_t elems_per_clip,
                              int global_max, cudaStream_t stream);
 
+// Encoder stem (stem_conv.cu): out = gelu(conv1d(x, weight, bias, kernel 3, padding 1)), x = mel clamped at max - 8 on
+// load when max_keys is given (then mel is the front-end's output before launch_tc_finish).  n_mels 80, n_state % 128 == 0.
+cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, const uint32_t* tile_keys, int global_max, int64_t batch,
+                                   int n_frames, const float* weight, const float* bias, int n_state, float* out, cudaStream_t stream);
+
 uint64_t launches_so_far();
 void count_launch(unsigned n = 1);
 

@@ -1,0 +1,370 @@
+// Encoder stem behind the front-end: conv1 (kernel 3, padding 1) + GELU of Whisper's AudioEncoder
+// (reference whisper/model.py:179, :193: `x = F.gelu(self.conv1(x))`) as an implicit GEMM on the tcgen05 tensor cores,
+// with the last step of the log-mel normalisation - the clamp at max - 8 (whisper/audio.py:155) - folded into its
+// input load, so the front-end can hand over its un-clamped output and one max per utterance.
+//
+//   out[b, n, t] = gelu(bias[n] + sum_{c, k} W[n, c, k] x[b, c, t + k - 1]),   x = max(y, floor_b), x[.., -1] = x[.., T] = 0
+//
+// As a GEMM per 128-frame tile: D[128 channels, 128 frames] = sum over the three taps k of W_k[128 channels, n_mels]
+// X_k[n_mels, 128 frames], kind::tf32 (operands rounded to TF32 - what cudnn's convolution does with torch's default
+// allow_tf32 - fp32 accumulation in tensor memory).
+//   A = the CTA's 128-channel slice of the weights, all three taps: 240 columns of TENSOR MEMORY, written once per CTA;
+//   B = the input tile from shared memory, staged ONCE, transposed to K-major - [n_mels / 4][130 frames][4 mels]: every
+//       frame a 16-byte row, rows contiguous - so the operand of tap k is the same tile starting k rows (16 k bytes)
+//       further on: no im2col copy;
+//   D = two accumulators of 128 columns: the epilogue of a tile overlaps the MMAs of the next.
+// One persistent CTA per SM; CTAs with the other slices walk the same tiles at the same time, so the input comes from HBM
+// once.  13 warps: 4 epilogue (thread = channel: bias, GELU, 32-byte sector stores along the frame axis), 1 MMA issue,
+// 8 loaders (coalesced 16-byte loads, clamp, TF32 rounding, 4 x 4 register transpose, 16-byte shared stores) running up to
+// four tiles ahead.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.h"
+
+namespace b200mel {
+
+namespace {
+
+constexpr int kStemTile = 128;                  // frames per tile = MMA N
+constexpr int kStemRows = kStemTile + 2;        // + one frame either side (kernel 3, padding 1)
+constexpr int kStemN = 128;                     // channels per CTA = MMA M = TMEM lanes
+constexpr int kStemMels = 80;
+constexpr int kStemKChunks = kStemMels / 4;     // 16-byte K chunks (4 tf32)
+constexpr int kStemChunkBytes = kStemRows * 16; // 2080: one K chunk of the tile
+constexpr int kStemXBytes = kStemKChunks * kStemChunkBytes;          // 41600 per input buffer (a multiple of 128)
+constexpr int kStemStages = 4;
+constexpr int kStemSmem = kStemStages * kStemXBytes;
+constexpr int kStemWarps = 13, kStemThreads = kStemWarps * 32;
+constexpr int kStemLoaderWarps = 8;
+constexpr int kStemWCols = 3 * kStemMels;       // tensor-memory columns of the weights: column = tap * 80 + mel
+constexpr int kStemDCol = 256;                  // the two accumulators: columns 256-383, 384-511
+constexpr uint32_t kStemIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kStemTile >> 3) << 17) |
+                                (static_cast<uint32_t>(kStemN >> 4) << 24);   // tf32 x tf32 -> f32, K-major, M 128, N 128
+static_assert(kStemXBytes % 128 == 0 && kStemSmem <= 227 * 1024, "shared memory layout");
+static_assert(kStemWCols <= kStemDCol, "tensor memory layout");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        if (done || ++spins > (1u << 17)) break;   // (a protocol bug ends the kernel with garbage instead of hanging the device)
+    }
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {      // round to nearest (ties away), as cudnn / cuBLAS do
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// K-major, no-swizzle operand: rows of 16 bytes, 8-row groups 128 bytes apart (i.e. rows contiguous), K chunks `lbo` bytes apart
+__device__ __forceinline__ uint64_t stem_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (static_cast<uint64_t>(0x4008u) << 32) | ((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, bool accumulate) {
+    asm volatile("{\n.reg .pred P, Q;\nelect.sync _|P, 0xffffffff;\nsetp.ne.u32 Q, %4, 0;\n"
+                 "@P tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, Q;\n}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kStemIdesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\n@P tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t t, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(t), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t t, float* d) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(t) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(r[i]);
+}
+
+// GELU(v) = v Phi(v) = h + |h| erf(|h| sqrt 2), h = v / 2, with erfc(u) = 2^(-u q(u)) on [0, 4.3] (beyond: < 2e-9):
+// q a degree-6 fit (tools/fit_gelu.py: |erfc error| 4.5e-7, |GELU error| <= 8.2e-8 for every v - below float32's spacing
+// at 1) - one MUFU and nine FMA-pipe instructions instead of erff's two dozen.  `h` = half the pre-activation.
+__device__ __forceinline__ float gelu_from_half(float h) {
+    const float a = fabsf(h);
+    const float u = fminf(a * 1.41421356237309515f, 4.3f);
+    float q = -5.393774335971102e-05f;
+    q = fmaf(q, u, 0.00014493041089735925f);
+    q = fmaf(q, u, 0.0031301151029765606f);
+    q = fmaf(q, u, -0.03049657866358757f);
+    q = fmaf(q, u, 0.14962077140808105f);
+    q = fmaf(q, u, 0.918138325214386f);
+    q = fmaf(q, u, 1.6279326677322388f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * q));
+    return fmaf(-a, e, h + a);       // h + |h| (1 - erfc): NaN stays NaN
+}
+
+struct StemBarriers { uint64_t x_full[kStemStages], x_empty[kStemStages], d_full[2], d_empty[2]; };
+
+struct StemArgs {
+    const float* mel;          // [batch, 80, n_frames]: y = (log10 + 4) / 4, clamped or not
+    const uint32_t* max_keys;  // [batch] ([1] with global_max) order-preserving keys of the max log10 (the front-end's workspace), or nullptr: `mel` is final
+    const uint32_t* tile_keys; // [batch * tiles][2] or nullptr: a tile whose max key is 0 was never stored by the front-end (all its samples were zero)
+    int global_max;
+    const float* weight;       // [n_state, 80, 3] (torch Conv1d layout)
+    const float* bias;         // [n_state]
+    float* out;                // [batch, n_state, n_frames]
+    int64_t batch;
+    int n_frames, n_state;
+    int vector_io;             // n_frames % 8 == 0 and 32-byte aligned pointers: 16-byte loads, 32-byte stores
+};
+
+// clamp of audio.py:155 in the (x + 4) / 4 domain, then TF32
+__device__ __forceinline__ uint32_t stem_input(float y, float floor_y) {
+    return to_tf32(floor_y != floor_y ? floor_y : (y < floor_y ? floor_y : y));
+}
+
+__global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const StemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) StemBarriers bars;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    const int slices = a.n_state / kStemN;
+    const int slice = blockIdx.x % slices;                       // this CTA's 128 channels
+    const int walkers = gridDim.x / slices;                      // CTAs that share the tiles of a slice
+    const int walker = blockIdx.x / slices;
+    const int tiles_per_clip = (a.n_frames + kStemTile - 1) / kStemTile;
+    const int64_t total_tiles = a.batch * tiles_per_clip;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < kStemStages; ++i) {
+            mbar_init(&bars.x_full[i], kStemLoaderWarps);
+            mbar_init(&bars.x_empty[i], 1);      // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.d_full[i], 1);       // tcgen05.commit
+            mbar_init(&bars.d_empty[i], 4);      // the four epilogue warps
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp < 4) {
+        // the slice's weights into tensor memory: lane = channel, column = tap * 80 + mel
+        const float* w = a.weight + (static_cast<int64_t>(slice) * kStemN + warp * 32 + lane) * kStemWCols;
+        const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+        for (int m = 0; m < kStemWCols / 8; ++m) {
+            const int tap = (8 * m) / kStemMels, c0 = (8 * m) % kStemMels;
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = to_tf32(__ldg(w + (c0 + i) * 3 + tap));
+            tmem_st8(lane_addr + 8 * m, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    if (warp >= 5) {
+        // ===== loaders: one tile [80 mels x 130 frames], clamped, rounded and transposed to [mel / 4][frame][mel % 4] =====
+        const int lw = warp - 5, lt = tid - 5 * 32;
+        const int q_in = lane & 3, g_in = lane >> 2;             // 4 mel quads x 8 frame groups per warp item
+        uint32_t parity = 1;                                     // x_empty: the first waits pass
+        int stage = 0;
+        for (int64_t tile = walker; tile < total_tiles; tile += walkers) {
+            const int64_t clip = tile / tiles_per_clip;
+            const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kStemTile;
+            float floor_y = __uint_as_float(0xff800000u);        // -inf: no clamp
+            if (a.max_keys != nullptr) {
+                const uint32_t key = __ldg(a.max_keys + (a.global_max ? 0 : clip));
+                const float g = key == 0u ? -10.0f : max_key_decode(key);
+                floor_y = ((g - 8.0f) + 4.0f) * 0.25f;
+            }
+            const uint32_t* tk = a.tile_keys != nullptr ? a.tile_keys + 2 * tile : nullptr;
+            const bool silent = tk != nullptr && __ldg(tk) == 0u;                 // never written: (log10(1e-10) + 4) / 4 everywhere
+            const float* src = a.mel + clip * kStemMels * static_cast<int64_t>(a.n_frames);
+            const bool whole = a.vector_io && t0 + kStemTile <= a.n_frames;
+            // 20 warp items (5 blocks of 4 mel quads x 4 blocks of 8 frame groups) over 8 warps: all loads first
+            float4 v[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int item = lw + kStemLoaderWarps * r;
+                if (item < 20) {
+                    const int q = (item % 5) * 4 + q_in, t = t0 + 4 * ((item / 5) * 8 + g_in);
+                    const float* p = src + static_cast<int64_t>(4 * q) * a.n_frames + t;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        if (silent) {
+                            v[r][m] = make_float4(-1.5f, -1.5f, -1.5f, -1.5f);
+                        } else if (whole) {
+                            v[r][m] = __ldg(reinterpret_cast<const float4*>(p + static_cast<int64_t>(m) * a.n_frames));
+                        } else {
+                            float e[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) e[j] = t + j < a.n_frames ? __ldg(p + static_cast<int64_t>(m) * a.n_frames + j) : 0.f;
+                            v[r][m] = make_float4(e[0], e[1], e[2], e[3]);
+                        }
+                    }
+                }
+            }
+            // the frame before and the frame behind the tile (the convolution's zero padding at the ends of the clip)
+            float halo = 0.f;
+            bool halo_inside = false;
+            if (lt < 2 * kStemMels) {
+                const int c = lt % kStemMels, side = lt / kStemMels;
+                const int t = side ? t0 + kStemTile : t0 - 1;
+                halo_inside = t >= 0 && t < a.n_frames;
+                if (halo_inside) {
+                    const bool halo_silent = tk != nullptr && __ldg(tk + (side ? 2 : -2)) == 0u;
+                    halo = halo_silent ? -1.5f : __ldg(src + static_cast<int64_t>(c) * a.n_frames + t);
+                }
+            }
+            mbar_wait(&bars.x_empty[stage], parity);
+            unsigned char* xs = smem_raw + stage * kStemXBytes;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int item = lw + kStemLoaderWarps * r;
+                if (item < 20) {
+                    const int q = (item % 5) * 4 + q_in, f = 4 * ((item / 5) * 8 + g_in);       // frame inside the tile; row = f + 1
+                    const float e[4][4] = {{v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w}, {v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w},
+                                           {v[r][2].x, v[r][2].y, v[r][2].z, v[r][2].w}, {v[r][3].x, v[r][3].y, v[r][3].z, v[r][3].w}};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 row;
+                        if (t0 + f + j < a.n_frames) {
+                            row = make_uint4(stem_input(e[0][j], floor_y), stem_input(e[1][j], floor_y), stem_input(e[2][j], floor_y),
+                                             stem_input(e[3][j], floor_y));
+                        } else {
+                            row = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        *reinterpret_cast<uint4*>(xs + q * kStemChunkBytes + (f + j + 1) * 16) = row;
+                    }
+                }
+            }
+            if (lt < 2 * kStemMels) {
+                const int c = lt % kStemMels, side = lt / kStemMels;
+                *reinterpret_cast<uint32_t*>(xs + (c >> 2) * kStemChunkBytes + (side ? kStemRows - 1 : 0) * 16 + (c & 3) * 4) =
+                    halo_inside ? stem_input(halo, floor_y) : 0u;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.x_full[stage]);
+            if (++stage == kStemStages) { stage = 0; parity ^= 1u; }
+        }
+    } else if (warp == 4) {
+        // ===== MMA issue: 3 taps x 10 K steps of 8 per tile =====
+        uint32_t x_parity = 0, d_parity = 1;                     // d_empty: the first two waits pass
+        int stage = 0, buf = 0;
+        for (int64_t tile = walker; tile < total_tiles; tile += walkers) {
+            mbar_wait(&bars.x_full[stage], x_parity);
+            mbar_wait(&bars.d_empty[buf], d_parity);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t x_addr = smem_u32(smem_raw + stage * kStemXBytes);
+            const uint32_t d_tmem = tmem + kStemDCol + buf * kStemTile;
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k)
+#pragma unroll 1
+                for (int j = 0; j < kStemMels / 8; ++j)          // K = 8 tf32 per MMA = two 16-byte chunks
+                    mma_tf32_ts(d_tmem, tmem + k * kStemMels + 8 * j, stem_desc(x_addr + 16 * k + 2 * j * kStemChunkBytes, kStemChunkBytes), k + j > 0);
+            mma_commit(&bars.d_full[buf]);
+            mma_commit(&bars.x_empty[stage]);
+            if (++stage == kStemStages) { stage = 0; x_parity ^= 1u; }
+            buf ^= 1;
+            if (buf == 0) d_parity ^= 1u;
+        }
+    } else {
+        // ===== epilogue: thread = channel (TMEM lane), 128 frames in pieces of 32: bias, GELU, 32-byte sector stores =====
+        uint32_t parity = 0;
+        int buf = 0;
+        const int n = warp * 32 + lane;
+        const float half_bias = 0.5f * __ldg(a.bias + slice * kStemN + n);
+        const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16) + kStemDCol;
+        for (int64_t tile = walker; tile < total_tiles; tile += walkers) {
+            const int64_t clip = tile / tiles_per_clip;
+            const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kStemTile;
+            float* out = a.out + (clip * a.n_state + static_cast<int64_t>(slice) * kStemN + n) * a.n_frames + t0;
+            mbar_wait(&bars.d_full[buf], parity);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int piece = 0; piece < kStemTile / 32; ++piece) {
+                float d[32];
+                tmem_ld32(lane_addr + buf * kStemTile + piece * 32, d);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (piece == kStemTile / 32 - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.d_empty[buf]);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) d[i] = gelu_from_half(fmaf(d[i], 0.5f, half_bias));
+                const int t = t0 + piece * 32;
+                if (a.vector_io) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8)
+                        if (t + i < a.n_frames)   // (n_frames % 8 == 0: a group of 8 is inside or outside as a whole)
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + piece * 32 + i), "f"(d[i]), "f"(d[i + 1]),
+                                         "f"(d[i + 2]), "f"(d[i + 3]), "f"(d[i + 4]), "f"(d[i + 5]), "f"(d[i + 6]), "f"(d[i + 7]) : "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (t + i < a.n_frames) out[piece * 32 + i] = d[i];
+                }
+            }
+            buf ^= 1;
+            if (buf == 0) parity ^= 1u;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace
+
+cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, const uint32_t* tile_keys, int global_max, int64_t batch, int n_frames, const float* weight,
+                                   const float* bias, int n_state, float* out, cudaStream_t stream) {
+    if (batch <= 0 || n_frames <= 0) return cudaSuccess;
+    static bool configured = false;
+    cudaError_t err;
+    if (!configured) {
+        err = cudaFuncSetAttribute(stem_conv1_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
+        if (err != cudaSuccess) return err;
+        configured = true;
+    }
+    int device = 0, sms = 0;
+    err = cudaGetDevice(&device);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err != cudaSuccess) return err;
+    const int slices = n_state / kStemN;
+    const int64_t tiles = batch * ((n_frames + kStemTile - 1) / kStemTile);
+    int64_t walkers = sms / slices;                                   // CTAs per slice; every CTA of the grid is resident
+    if (walkers < 1) walkers = 1;
+    if (walkers > tiles) walkers = tiles;
+    const int vector_io = n_frames % 8 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 32 == 0;
+    StemArgs a{mel, max_keys, tile_keys, global_max, weight, bias, out, batch, n_frames, n_state, vector_io};
+    ProfileScope profile(3, stream);
+    stem_conv1_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kStemThreads, kStemSmem, stream>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b200mel

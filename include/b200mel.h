@@ -73,6 +73,11 @@ typedef enum b200mel_variant {
                                       .to(dtype)); half the write bytes.  tcgen05 variant only - otherwise
                                       B200MEL_ERR_BAD_ARGUMENT.                                                   */
 
+#define B200MEL_FLAG_DEFER_CLAMP 8u /* tcgen05 variant, float32 output: leave `out` BEFORE the clamp at max - 8 (audio.py:155) -
+                                      (log10 + 4) / 4 un-clamped, all-zero tiles not written at all with B200MEL_FLAG_TILE_KEYS -
+                                      for a consumer that applies the clamp on load from `workspace`:
+                                      b200mel_stem_conv1_gelu_device.  Saves the clamp's second touch of the output.   */
+
 typedef struct b200mel_plan b200mel_plan; /* opaque: filterbank bands + FFT tables on one device */
 
 int b200mel_abi_version(void);
@@ -118,6 +123,21 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
  * (audio.py:155-156).  Exposed for tests; b200mel_logmel_device already runs it. */
 int b200mel_normalise_device(float* out, const void* workspace, int64_t batch, int64_t elems_per_clip,
                              unsigned flags, void* stream);
+
+/* The consumer right behind the front-end: the encoder stem's first layer, model.py:179 + :193
+ *   out = F.gelu(conv1(x)),  conv1 = Conv1d(n_mels, n_state, kernel_size=3, padding=1)
+ * as an implicit GEMM on the tcgen05 tensor cores (TF32 operands, float32 accumulation - what torch's own conv does on
+ * this GPU with allow_tf32, cudnn's default), exact (erf) GELU.
+ *   mel        device float32 [batch, n_mels, n_frames]
+ *   workspace  NULL: `mel` is a finished log-mel spectrogram.  Otherwise the workspace of the b200mel_logmel_device call
+ *              that produced `mel` with B200MEL_FLAG_DEFER_CLAMP; `flags` = that call's (GLOBAL_MAX, TILE_KEYS): the
+ *              clamp is applied while loading, never-written all-zero tiles are not read
+ *   weight     device float32 [n_state, n_mels, 3] (torch Conv1d.weight), bias [n_state]
+ *   out        device float32 [batch, n_state, n_frames]
+ * n_mels must be 80 (else B200MEL_ERR_BAD_N_MELS), n_state a multiple of 128 (Whisper's: 384 tiny, 512 base, 768 small, 1024 medium, 1280 large). */
+int b200mel_stem_conv1_gelu_device(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels,
+                                   int64_t n_frames, const float* weight, const float* bias, int n_state, float* out,
+                                   void* stream);
 
 /* Host-buffer entry point (what a CPU-tensor caller of log_mel_spectrogram hits, audio.py:138-144):
  * audio_host / out_host are HOST pointers (pinned for full speed).  Copies in, computes and copies
