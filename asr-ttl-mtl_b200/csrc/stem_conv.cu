@@ -14,7 +14,7 @@
 //       further on: no im2col copy;
 //   D = two accumulators of 128 columns: the epilogue of a tile overlaps the MMAs of the next.
 // One persistent CTA per SM; CTAs with the other slices walk the same tiles at the same time, so the input comes from HBM
-// once.  13 warps: 4 epilogue (thread = channel: bias, GELU, 32-byte sector stores along the frame axis), 1 MMA issue,
+// once.  17 warps: 2 x 4 epilogue (thread = channel: bias, GELU, 32-byte sector stores along the frame axis), 1 MMA issue,
 // 8 loaders (coalesced 16-byte loads, clamp, TF32 rounding, 4 x 4 register transpose, 16-byte shared stores) running up to
 // four tiles ahead.
 #include <cuda_runtime.h>
@@ -36,8 +36,8 @@ constexpr int kStemChunkBytes = kStemRows * 16; // 2080: one K chunk of the tile
 constexpr int kStemXBytes = kStemKChunks * kStemChunkBytes;          // 41600 per input buffer (a multiple of 128)
 constexpr int kStemStages = 4;
 constexpr int kStemSmem = kStemStages * kStemXBytes;
-constexpr int kStemWarps = 13, kStemThreads = kStemWarps * 32;
-constexpr int kStemLoaderWarps = 8;
+constexpr int kStemWarpMma = 8, kStemLoaderWarps = 8;   // warps 0-7 epilogue, 8 MMA issue, 9-16 loaders
+constexpr int kStemWarps = kStemWarpMma + 1 + kStemLoaderWarps, kStemThreads = kStemWarps * 32;
 constexpr int kStemWCols = 3 * kStemMels;       // tensor-memory columns of the weights: column = tap * 80 + mel
 constexpr int kStemDCol = 256;                  // the two accumulators: columns 256-383, 384-511
 constexpr uint32_t kStemIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kStemTile >> 3) << 17) |
@@ -58,6 +58,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
         if (done || ++spins > (1u << 17)) break;   // (a protocol bug ends the kernel with garbage instead of hanging the device)
+    }
+}
+// for the roles that run several tiles ahead: back off between polls instead of taking issue slots from the epilogue
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done || ++spins > (1u << 22)) break;
+        __nanosleep(400);
     }
 }
 __device__ __forceinline__ uint32_t to_tf32(float x) {      // round to nearest (ties away), as cudnn / cuBLAS do
@@ -130,8 +140,12 @@ struct StemArgs {
 };
 
 // clamp of audio.py:155 in the (x + 4) / 4 domain, then TF32
+// (max.NaN keeps a NaN of either side, like torch.maximum; the tensor core drops the low 13 bits of what it reads, so
+// adding half a TF32 ulp to the bit pattern of a finite value is round-to-nearest, ties away - what cvt.rna.tf32.f32 does,
+// without its final mask.  Not for NaN: max.NaN returns 0x7fffffff, which the add would wrap to a denormal.)
 __device__ __forceinline__ uint32_t stem_input(float y, float floor_y) {
-    return to_tf32(floor_y != floor_y ? floor_y : (y < floor_y ? floor_y : y));
+    const float m = max_nan(y, floor_y);
+    return __float_as_uint(m) + (fabsf(m) < __uint_as_float(0x7f800000u) ? 0x1000u : 0u);
 }
 
 __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const StemArgs a) {
@@ -157,7 +171,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars.d_full[i], 1);       // tcgen05.commit
-            mbar_init(&bars.d_empty[i], 4);      // the four epilogue warps
+            mbar_init(&bars.d_empty[i], 4);      // the accumulator's four epilogue warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -184,9 +198,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    if (warp >= 5) {
+    if (warp > kStemWarpMma) {
         // ===== loaders: one tile [80 mels x 130 frames], clamped, rounded and transposed to [mel / 4][frame][mel % 4] =====
-        const int lw = warp - 5, lt = tid - 5 * 32;
+        const int lw = warp - kStemWarpMma - 1, lt = tid - (kStemWarpMma + 1) * 32;
         const int q_in = lane & 3, g_in = lane >> 2;             // 4 mel quads x 8 frame groups per warp item
         uint32_t parity = 1;                                     // x_empty: the first waits pass
         int stage = 0;
@@ -202,30 +216,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
             const uint32_t* tk = a.tile_keys != nullptr ? a.tile_keys + 2 * tile : nullptr;
             const bool silent = tk != nullptr && __ldg(tk) == 0u;                 // never written: (log10(1e-10) + 4) / 4 everywhere
             const float* src = a.mel + clip * kStemMels * static_cast<int64_t>(a.n_frames);
-            const bool whole = a.vector_io && t0 + kStemTile <= a.n_frames;
-            // 20 warp items (5 blocks of 4 mel quads x 4 blocks of 8 frame groups) over 8 warps: all loads first
-            float4 v[3][4];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int item = lw + kStemLoaderWarps * r;
-                if (item < 20) {
-                    const int q = (item % 5) * 4 + q_in, t = t0 + 4 * ((item / 5) * 8 + g_in);
-                    const float* p = src + static_cast<int64_t>(4 * q) * a.n_frames + t;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        if (silent) {
-                            v[r][m] = make_float4(-1.5f, -1.5f, -1.5f, -1.5f);
-                        } else if (whole) {
-                            v[r][m] = __ldg(reinterpret_cast<const float4*>(p + static_cast<int64_t>(m) * a.n_frames));
-                        } else {
-                            float e[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) e[j] = t + j < a.n_frames ? __ldg(p + static_cast<int64_t>(m) * a.n_frames + j) : 0.f;
-                            v[r][m] = make_float4(e[0], e[1], e[2], e[3]);
-                        }
-                    }
-                }
-            }
+            unsigned char* xs = smem_raw + stage * kStemXBytes;
             // the frame before and the frame behind the tile (the convolution's zero padding at the ends of the clip)
             float halo = 0.f;
             bool halo_inside = false;
@@ -238,26 +229,45 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                     halo = halo_silent ? -1.5f : __ldg(src + static_cast<int64_t>(c) * a.n_frames + t);
                 }
             }
-            mbar_wait(&bars.x_empty[stage], parity);
-            unsigned char* xs = smem_raw + stage * kStemXBytes;
+            if (a.vector_io) {
+                // 20 warp items (5 blocks of 4 mel quads x 4 blocks of 8 frame groups of 4) over 8 warps; all loads first.
+                // n_frames % 4 == 0: a group of 4 frames is inside the clip or outside as a whole.
+                float4 v[3][4];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int item = lw + kStemLoaderWarps * r;
-                if (item < 20) {
-                    const int q = (item % 5) * 4 + q_in, f = 4 * ((item / 5) * 8 + g_in);       // frame inside the tile; row = f + 1
-                    const float e[4][4] = {{v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w}, {v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w},
-                                           {v[r][2].x, v[r][2].y, v[r][2].z, v[r][2].w}, {v[r][3].x, v[r][3].y, v[r][3].z, v[r][3].w}};
+                for (int r = 0; r < 3; ++r) {
+                    const int item = lw + kStemLoaderWarps * r;
+                    const int q = (item % 5) * 4 + q_in, t = t0 + 4 * ((item / 5) * 8 + g_in);
+                    const float* p = src + static_cast<int64_t>(4 * q) * a.n_frames + t;
+                    const bool load = item < 20 && !silent && t < a.n_frames;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 row;
-                        if (t0 + f + j < a.n_frames) {
-                            row = make_uint4(stem_input(e[0][j], floor_y), stem_input(e[1][j], floor_y), stem_input(e[2][j], floor_y),
-                                             stem_input(e[3][j], floor_y));
-                        } else {
-                            row = make_uint4(0u, 0u, 0u, 0u);
-                        }
-                        *reinterpret_cast<uint4*>(xs + q * kStemChunkBytes + (f + j + 1) * 16) = row;
+                    for (int m = 0; m < 4; ++m) {
+                        v[r][m] = silent ? make_float4(-1.5f, -1.5f, -1.5f, -1.5f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (load) v[r][m] = __ldg(reinterpret_cast<const float4*>(p + static_cast<int64_t>(m) * a.n_frames));
                     }
+                }
+                mbar_wait_relaxed(&bars.x_empty[stage], parity);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int item = lw + kStemLoaderWarps * r;
+                    if (item < 20) {
+                        const int q = (item % 5) * 4 + q_in, f = 4 * ((item / 5) * 8 + g_in);   // frame inside the tile; row = f + 1
+                        const bool inside = t0 + f < a.n_frames;
+                        uint4* dst = reinterpret_cast<uint4*>(xs + q * kStemChunkBytes + (f + 1) * 16);
+                        dst[0] = inside ? make_uint4(stem_input(v[r][0].x, floor_y), stem_input(v[r][1].x, floor_y), stem_input(v[r][2].x, floor_y), stem_input(v[r][3].x, floor_y)) : make_uint4(0u, 0u, 0u, 0u);
+                        dst[1] = inside ? make_uint4(stem_input(v[r][0].y, floor_y), stem_input(v[r][1].y, floor_y), stem_input(v[r][2].y, floor_y), stem_input(v[r][3].y, floor_y)) : make_uint4(0u, 0u, 0u, 0u);
+                        dst[2] = inside ? make_uint4(stem_input(v[r][0].z, floor_y), stem_input(v[r][1].z, floor_y), stem_input(v[r][2].z, floor_y), stem_input(v[r][3].z, floor_y)) : make_uint4(0u, 0u, 0u, 0u);
+                        dst[3] = inside ? make_uint4(stem_input(v[r][0].w, floor_y), stem_input(v[r][1].w, floor_y), stem_input(v[r][2].w, floor_y), stem_input(v[r][3].w, floor_y)) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+            } else {
+                // any n_frames / alignment: element by element (consecutive threads along the frame axis)
+                mbar_wait_relaxed(&bars.x_empty[stage], parity);
+#pragma unroll 1
+                for (int i = lt; i < kStemMels * kStemTile; i += kStemLoaderWarps * 32) {
+                    const int c = i / kStemTile, f = i % kStemTile;
+                    uint32_t x = 0u;
+                    if (t0 + f < a.n_frames) x = stem_input(silent ? -1.5f : __ldg(src + static_cast<int64_t>(c) * a.n_frames + t0 + f), floor_y);
+                    *reinterpret_cast<uint32_t*>(xs + (c >> 2) * kStemChunkBytes + (f + 1) * 16 + (c & 3) * 4) = x;
                 }
             }
             if (lt < 2 * kStemMels) {
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
             if (lane == 0) mbar_arrive(&bars.x_full[stage]);
             if (++stage == kStemStages) { stage = 0; parity ^= 1u; }
         }
-    } else if (warp == 4) {
+    } else if (warp == kStemWarpMma) {
         // ===== MMA issue: 3 taps x 10 K steps of 8 per tile =====
         uint32_t x_parity = 0, d_parity = 1;                     // d_empty: the first two waits pass
         int stage = 0, buf = 0;
@@ -292,22 +302,24 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
             if (buf == 0) d_parity ^= 1u;
         }
     } else {
-        // ===== epilogue: thread = channel (TMEM lane), 128 frames in pieces of 32: bias, GELU, 32-byte sector stores =====
+        // ===== epilogue: two warps per TMEM lane quadrant, one per accumulator - they take the CTA's tiles in turn.
+        // thread = channel, 128 frames in pieces of 32: bias, GELU, 32-byte sector stores =====
+        const int buf = warp >> 2;
         uint32_t parity = 0;
-        int buf = 0;
-        const int n = warp * 32 + lane;
+        const int n = (warp & 3) * 32 + lane;
         const float half_bias = 0.5f * __ldg(a.bias + slice * kStemN + n);
-        const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16) + kStemDCol;
-        for (int64_t tile = walker; tile < total_tiles; tile += walkers) {
+        const uint32_t d_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kStemDCol + buf * kStemTile;
+        for (int64_t tile = walker + static_cast<int64_t>(buf) * walkers; tile < total_tiles; tile += 2 * static_cast<int64_t>(walkers)) {
             const int64_t clip = tile / tiles_per_clip;
             const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kStemTile;
             float* out = a.out + (clip * a.n_state + static_cast<int64_t>(slice) * kStemN + n) * a.n_frames + t0;
             mbar_wait(&bars.d_full[buf], parity);
+            parity ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int piece = 0; piece < kStemTile / 32; ++piece) {
                 float d[32];
-                tmem_ld32(lane_addr + buf * kStemTile + piece * 32, d);
+                tmem_ld32(d_addr + piece * 32, d);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (piece == kStemTile / 32 - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -329,8 +341,6 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                         if (t + i < a.n_frames) out[piece * 32 + i] = d[i];
                 }
             }
-            buf ^= 1;
-            if (buf == 0) parity ^= 1u;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
