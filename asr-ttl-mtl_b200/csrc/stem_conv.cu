@@ -14,10 +14,14 @@
 //       further on: no im2col copy;
 //   D = two accumulators of 128 columns: the epilogue of a tile overlaps the MMAs of the next.
 // One persistent CTA per SM; CTAs with the other slices walk the same tiles at the same time, so the input comes from HBM
-// once.  17 warps: 2 x 4 epilogue (thread = channel: bias, GELU, 32-byte sector stores along the frame axis), 1 MMA issue,
-// 8 loaders (coalesced 16-byte loads, clamp, TF32 rounding, 4 x 4 register transpose, 16-byte shared stores) running up to
-// four tiles ahead.
+// once.  25 warps: 2 x 4 epilogue (thread = channel: bias, GELU, the 32 x 32 piece through a swizzled shared-memory buffer
+// and out with a TMA tensor store - full lines, no L1 tag traffic), 1 MMA issue, 2 x 8 loaders (coalesced 16-byte loads,
+// clamp, TF32 rounding, 4 x 4 register transpose, 16-byte shared stores; the two groups take the tiles in turn so that one
+// group's DRAM round trip hides behind the other's transposition).
+#include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <cstring>
 
 #include <cstdint>
 
@@ -34,10 +38,12 @@ constexpr int kStemMels = 80;
 constexpr int kStemKChunks = kStemMels / 4;     // 16-byte K chunks (4 tf32)
 constexpr int kStemChunkBytes = kStemRows * 16; // 2080: one K chunk of the tile
 constexpr int kStemXBytes = kStemKChunks * kStemChunkBytes;          // 41600 per input buffer (a multiple of 128)
-constexpr int kStemStages = 4;
-constexpr int kStemSmem = kStemStages * kStemXBytes;
-constexpr int kStemWarpMma = 8, kStemLoaderWarps = 8;   // warps 0-7 epilogue, 8 MMA issue, 9-16 loaders
-constexpr int kStemWarps = kStemWarpMma + 1 + kStemLoaderWarps, kStemThreads = kStemWarps * 32;
+constexpr int kStemStages = 3;
+constexpr int kStemWarpMma = 8, kStemLoaderWarps = 8, kStemLoaderGroups = 2;   // warps 0-7 epilogue, 8 MMA issue, 9-24 loaders
+constexpr int kStemWarps = kStemWarpMma + 1 + kStemLoaderGroups * kStemLoaderWarps, kStemThreads = kStemWarps * 32;
+constexpr int kStemPieceBytes = 32 * 32 * 4;    // an epilogue warp's 32 channels x 32 frames on their way out
+constexpr int kStemOutOffset = (kStemStages * kStemXBytes + 1023) / 1024 * 1024;   // (128-byte swizzle: 1024-byte aligned)
+constexpr int kStemSmem = kStemOutOffset + kStemWarpMma * 2 * kStemPieceBytes + 1024;   // + slack to align the base
 constexpr int kStemWCols = 3 * kStemMels;       // tensor-memory columns of the weights: column = tap * 80 + mel
 constexpr int kStemDCol = 256;                  // the two accumulators: columns 256-383, 384-511
 constexpr uint32_t kStemIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kStemTile >> 3) << 17) |
@@ -61,13 +67,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 // for the roles that run several tiles ahead: back off between polls instead of taking issue slots from the epilogue
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned sleep_ns) {
     uint32_t done = 0, spins = 0;
     while (true) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done || ++spins > (1u << 22)) break;
-        __nanosleep(400);
+        __nanosleep(sleep_ns);
     }
 }
 __device__ __forceinline__ uint32_t to_tf32(float x) {      // round to nearest (ties away), as cudnn / cuBLAS do
@@ -124,6 +130,17 @@ __device__ __forceinline__ float gelu_from_half(float h) {
     return fmaf(-a, e, h + a);       // h + |h| (1 - erfc): NaN stays NaN
 }
 
+// (clip, tile inside the clip) of a CTA's k-th tile, advanced by the grid's stride without a division
+struct TileStep { int clips, tiles, tiles_per_clip; };
+struct TileWalk {
+    int clip, tile;
+    __device__ __forceinline__ void advance(const TileStep& s) {
+        clip += s.clips;
+        tile += s.tiles;
+        if (tile >= s.tiles_per_clip) { tile -= s.tiles_per_clip; ++clip; }
+    }
+};
+
 struct StemBarriers { uint64_t x_full[kStemStages], x_empty[kStemStages], d_full[2], d_empty[2]; };
 
 struct StemArgs {
@@ -136,7 +153,7 @@ struct StemArgs {
     float* out;                // [batch, n_state, n_frames]
     int64_t batch;
     int n_frames, n_state;
-    int vector_io;             // n_frames % 8 == 0 and 32-byte aligned pointers: 16-byte loads, 32-byte stores
+    int vector_io;             // n_frames % 4 == 0 and 16-byte aligned pointers: 16-byte loads, TMA tensor stores
 };
 
 // clamp of audio.py:155 in the (x + 4) / 4 domain, then TF32
@@ -148,8 +165,9 @@ __device__ __forceinline__ uint32_t stem_input(float y, float floor_y) {
     return __float_as_uint(m) + (fabsf(m) < __uint_as_float(0x7f800000u) ? 0x1000u : 0u);
 }
 
-__global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const StemArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const StemArgs a, const __grid_constant__ CUtensorMap out_map) {
+    extern __shared__ unsigned char smem_unaligned[];
+    unsigned char* const smem_raw = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
     __shared__ __align__(8) StemBarriers bars;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -198,103 +216,134 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
+    // this CTA's tiles: walker, walker + walkers, ... - (clip, tile inside the clip) advance without a division per tile
+    const int my_tiles = walker < total_tiles ? static_cast<int>((total_tiles - walker + walkers - 1) / walkers) : 0;
+    const TileWalk first{walker / tiles_per_clip, walker % tiles_per_clip};
+    const TileStep step{walkers / tiles_per_clip, walkers % tiles_per_clip, tiles_per_clip};
+
     if (warp > kStemWarpMma) {
-        // ===== loaders: one tile [80 mels x 130 frames], clamped, rounded and transposed to [mel / 4][frame][mel % 4] =====
-        const int lw = warp - kStemWarpMma - 1, lt = tid - (kStemWarpMma + 1) * 32;
+        // ===== loaders: one tile [80 mels x 130 frames], clamped, rounded and transposed to [mel / 4][frame][mel % 4];
+        // two groups of 8 warps, group g takes the CTA's tiles g, g + 2, ... =====
+        const int group = (warp - kStemWarpMma - 1) / kStemLoaderWarps;
+        const int lw = (warp - kStemWarpMma - 1) % kStemLoaderWarps, lt = lw * 32 + lane;
         const int q_in = lane & 3, g_in = lane >> 2;             // 4 mel quads x 8 frame groups per warp item
-        uint32_t parity = 1;                                     // x_empty: the first waits pass
-        int stage = 0;
-        for (int64_t tile = walker; tile < total_tiles; tile += walkers) {
-            const int64_t clip = tile / tiles_per_clip;
-            const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kStemTile;
+        // vector path: 20 warp items (5 blocks of 4 mel quads x 4 blocks of 8 frame groups of 4) over 8 warps
+        int item_f[3];
+        int64_t item_src[3];
+        uint32_t item_dst[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int item = lw + kStemLoaderWarps * r;
+            const int q = (item % 5) * 4 + q_in;
+            item_f[r] = 4 * ((item / 5) * 8 + g_in);             // frame inside the tile; row = f + 1
+            item_src[r] = static_cast<int64_t>(4 * q) * a.n_frames + item_f[r];
+            item_dst[r] = q * kStemChunkBytes + (item_f[r] + 1) * 16;
+        }
+        const bool third = lw + 2 * kStemLoaderWarps < 20;       // warps 0-3 have a third item
+        const int halo_c = lt % kStemMels, halo_side = lt / kStemMels;   // threads 0-159: the frame before / behind the tile
+        const uint32_t halo_dst = (halo_c >> 2) * kStemChunkBytes + (halo_side ? kStemRows - 1 : 0) * 16 + (halo_c & 3) * 4;
+        TileWalk w = first, ahead = first;
+        if (group) w.advance(step);
+        ahead = w;
+        ahead.advance(step);
+        ahead.advance(step);
+        for (int k = group; k < my_tiles; k += kStemLoaderGroups, w = ahead, ahead.advance(step), ahead.advance(step)) {
+            const int stage = k % kStemStages;
+            const uint32_t parity = ((k / kStemStages) & 1) ^ 1u;     // x_empty: the first use of a stage passes
+            const int t0 = w.tile * kStemTile;
+            const int64_t tile = static_cast<int64_t>(w.clip) * tiles_per_clip + w.tile;
             float floor_y = __uint_as_float(0xff800000u);        // -inf: no clamp
             if (a.max_keys != nullptr) {
-                const uint32_t key = __ldg(a.max_keys + (a.global_max ? 0 : clip));
+                const uint32_t key = __ldg(a.max_keys + (a.global_max ? 0 : w.clip));
                 const float g = key == 0u ? -10.0f : max_key_decode(key);
                 floor_y = ((g - 8.0f) + 4.0f) * 0.25f;
             }
             const uint32_t* tk = a.tile_keys != nullptr ? a.tile_keys + 2 * tile : nullptr;
             const bool silent = tk != nullptr && __ldg(tk) == 0u;                 // never written: (log10(1e-10) + 4) / 4 everywhere
-            const float* src = a.mel + clip * kStemMels * static_cast<int64_t>(a.n_frames);
+            const float* src = a.mel + (static_cast<int64_t>(w.clip) * kStemMels * a.n_frames + t0);
             unsigned char* xs = smem_raw + stage * kStemXBytes;
             // the frame before and the frame behind the tile (the convolution's zero padding at the ends of the clip)
             float halo = 0.f;
             bool halo_inside = false;
             if (lt < 2 * kStemMels) {
-                const int c = lt % kStemMels, side = lt / kStemMels;
-                const int t = side ? t0 + kStemTile : t0 - 1;
+                const int t = halo_side ? t0 + kStemTile : t0 - 1;
                 halo_inside = t >= 0 && t < a.n_frames;
                 if (halo_inside) {
-                    const bool halo_silent = tk != nullptr && __ldg(tk + (side ? 2 : -2)) == 0u;
-                    halo = halo_silent ? -1.5f : __ldg(src + static_cast<int64_t>(c) * a.n_frames + t);
+                    const bool halo_silent = tk != nullptr && __ldg(tk + (halo_side ? 2 : -2)) == 0u;
+                    halo = halo_silent ? -1.5f : __ldg(src + static_cast<int64_t>(halo_c) * a.n_frames + (t - t0));
                 }
             }
             if (a.vector_io) {
-                // 20 warp items (5 blocks of 4 mel quads x 4 blocks of 8 frame groups of 4) over 8 warps; all loads first.
-                // n_frames % 4 == 0: a group of 4 frames is inside the clip or outside as a whole.
+                // all loads first.  n_frames % 4 == 0: a group of 4 frames is inside the clip or outside as a whole.
                 float4 v[3][4];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const int item = lw + kStemLoaderWarps * r;
-                    const int q = (item % 5) * 4 + q_in, t = t0 + 4 * ((item / 5) * 8 + g_in);
-                    const float* p = src + static_cast<int64_t>(4 * q) * a.n_frames + t;
-                    const bool load = item < 20 && !silent && t < a.n_frames;
+                    const float* p = src + item_src[r];
+                    const bool load = (r < 2 || third) && !silent && t0 + item_f[r] < a.n_frames;
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
                         v[r][m] = silent ? make_float4(-1.5f, -1.5f, -1.5f, -1.5f) : make_float4(0.f, 0.f, 0.f, 0.f);
                         if (load) v[r][m] = __ldg(reinterpret_cast<const float4*>(p + static_cast<int64_t>(m) * a.n_frames));
                     }
                 }
-                mbar_wait_relaxed(&bars.x_empty[stage], parity);
+                // ask L2 for this thread's part of the group's next tile
+                if (k + kStemLoaderGroups < my_tiles) {
+                    const bool asilent = a.tile_keys != nullptr && __ldg(a.tile_keys + 2 * (static_cast<int64_t>(ahead.clip) * tiles_per_clip + ahead.tile)) == 0u;
+                    const float* asrc = a.mel + (static_cast<int64_t>(ahead.clip) * kStemMels * a.n_frames + ahead.tile * kStemTile);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        if ((r < 2 || third) && !asilent && ahead.tile * kStemTile + item_f[r] < a.n_frames) {
+#pragma unroll
+                            for (int m = 0; m < 4; ++m)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(asrc + item_src[r] + static_cast<int64_t>(m) * a.n_frames));
+                        }
+                    }
+                }
+                mbar_wait_relaxed(&bars.x_empty[stage], parity, 200);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const int item = lw + kStemLoaderWarps * r;
-                    if (item < 20) {
-                        const int q = (item % 5) * 4 + q_in, f = 4 * ((item / 5) * 8 + g_in);   // frame inside the tile; row = f + 1
-                        const bool inside = t0 + f < a.n_frames;
-                        uint4* dst = reinterpret_cast<uint4*>(xs + q * kStemChunkBytes + (f + 1) * 16);
-                        dst[0] = inside ? make_uint4(stem_input(v[r][0].x, floor_y), stem_input(v[r][1].x, floor_y), stem_input(v[r][2].x, floor_y), stem_input(v[r][3].x, floor_y)) : make_uint4(0u, 0u, 0u, 0u);
-                        dst[1] = inside ? make_uint4(stem_input(v[r][0].y, floor_y), stem_input(v[r][1].y, floor_y), stem_input(v[r][2].y, floor_y), stem_input(v[r][3].y, floor_y)) : make_uint4(0u, 0u, 0u, 0u);
-                        dst[2] = inside ? make_uint4(stem_input(v[r][0].z, floor_y), stem_input(v[r][1].z, floor_y), stem_input(v[r][2].z, floor_y), stem_input(v[r][3].z, floor_y)) : make_uint4(0u, 0u, 0u, 0u);
-                        dst[3] = inside ? make_uint4(stem_input(v[r][0].w, floor_y), stem_input(v[r][1].w, floor_y), stem_input(v[r][2].w, floor_y), stem_input(v[r][3].w, floor_y)) : make_uint4(0u, 0u, 0u, 0u);
+                    if (r < 2 || third) {
+                        const bool inside = t0 + item_f[r] < a.n_frames;
+                        uint4* dst = reinterpret_cast<uint4*>(xs + item_dst[r]);
+                        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                        dst[0] = inside ? make_uint4(stem_input(v[r][0].x, floor_y), stem_input(v[r][1].x, floor_y), stem_input(v[r][2].x, floor_y), stem_input(v[r][3].x, floor_y)) : zero;
+                        dst[1] = inside ? make_uint4(stem_input(v[r][0].y, floor_y), stem_input(v[r][1].y, floor_y), stem_input(v[r][2].y, floor_y), stem_input(v[r][3].y, floor_y)) : zero;
+                        dst[2] = inside ? make_uint4(stem_input(v[r][0].z, floor_y), stem_input(v[r][1].z, floor_y), stem_input(v[r][2].z, floor_y), stem_input(v[r][3].z, floor_y)) : zero;
+                        dst[3] = inside ? make_uint4(stem_input(v[r][0].w, floor_y), stem_input(v[r][1].w, floor_y), stem_input(v[r][2].w, floor_y), stem_input(v[r][3].w, floor_y)) : zero;
                     }
                 }
             } else {
                 // any n_frames / alignment: element by element (consecutive threads along the frame axis)
-                mbar_wait_relaxed(&bars.x_empty[stage], parity);
+                mbar_wait_relaxed(&bars.x_empty[stage], parity, 200);
 #pragma unroll 1
                 for (int i = lt; i < kStemMels * kStemTile; i += kStemLoaderWarps * 32) {
                     const int c = i / kStemTile, f = i % kStemTile;
                     uint32_t x = 0u;
-                    if (t0 + f < a.n_frames) x = stem_input(silent ? -1.5f : __ldg(src + static_cast<int64_t>(c) * a.n_frames + t0 + f), floor_y);
+                    if (t0 + f < a.n_frames) x = stem_input(silent ? -1.5f : __ldg(src + static_cast<int64_t>(c) * a.n_frames + f), floor_y);
                     *reinterpret_cast<uint32_t*>(xs + (c >> 2) * kStemChunkBytes + (f + 1) * 16 + (c & 3) * 4) = x;
                 }
             }
-            if (lt < 2 * kStemMels) {
-                const int c = lt % kStemMels, side = lt / kStemMels;
-                *reinterpret_cast<uint32_t*>(xs + (c >> 2) * kStemChunkBytes + (side ? kStemRows - 1 : 0) * 16 + (c & 3) * 4) =
-                    halo_inside ? stem_input(halo, floor_y) : 0u;
-            }
+            if (lt < 2 * kStemMels) *reinterpret_cast<uint32_t*>(xs + halo_dst) = halo_inside ? stem_input(halo, floor_y) : 0u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars.x_full[stage]);
-            if (++stage == kStemStages) { stage = 0; parity ^= 1u; }
         }
     } else if (warp == kStemWarpMma) {
         // ===== MMA issue: 3 taps x 10 K steps of 8 per tile =====
         uint32_t x_parity = 0, d_parity = 1;                     // d_empty: the first two waits pass
         int stage = 0, buf = 0;
-        for (int64_t tile = walker; tile < total_tiles; tile += walkers) {
-            mbar_wait(&bars.x_full[stage], x_parity);
-            mbar_wait(&bars.d_empty[buf], d_parity);
+        const uint32_t x_base = smem_u32(smem_raw);
+        for (int k = 0; k < my_tiles; ++k) {
+            mbar_wait_relaxed(&bars.x_full[stage], x_parity, 32);
+            mbar_wait_relaxed(&bars.d_empty[buf], d_parity, 32);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t x_addr = smem_u32(smem_raw + stage * kStemXBytes);
+            const uint64_t desc0 = stem_desc(x_base + stage * kStemXBytes, kStemChunkBytes);
             const uint32_t d_tmem = tmem + kStemDCol + buf * kStemTile;
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k)
-#pragma unroll 1
-                for (int j = 0; j < kStemMels / 8; ++j)          // K = 8 tf32 per MMA = two 16-byte chunks
-                    mma_tf32_ts(d_tmem, tmem + k * kStemMels + 8 * j, stem_desc(x_addr + 16 * k + 2 * j * kStemChunkBytes, kStemChunkBytes), k + j > 0);
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                for (int j = 0; j < kStemMels / 8; ++j)          // K = 8 tf32 per MMA = two 16-byte chunks; the tap moves the start by one row
+                    mma_tf32_ts(d_tmem, tmem + kk * kStemMels + 8 * j, desc0 + ((16 * kk + 2 * j * kStemChunkBytes) >> 4), kk + j > 0);
             mma_commit(&bars.d_full[buf]);
             mma_commit(&bars.x_empty[stage]);
             if (++stage == kStemStages) { stage = 0; x_parity ^= 1u; }
@@ -309,11 +358,19 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
         const int n = (warp & 3) * 32 + lane;
         const float half_bias = 0.5f * __ldg(a.bias + slice * kStemN + n);
         const uint32_t d_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kStemDCol + buf * kStemTile;
-        for (int64_t tile = walker + static_cast<int64_t>(buf) * walkers; tile < total_tiles; tile += 2 * static_cast<int64_t>(walkers)) {
-            const int64_t clip = tile / tiles_per_clip;
-            const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kStemTile;
-            float* out = a.out + (clip * a.n_state + static_cast<int64_t>(slice) * kStemN + n) * a.n_frames + t0;
-            mbar_wait(&bars.d_full[buf], parity);
+        float* const out_n = a.out + (static_cast<int64_t>(slice) * kStemN + n) * a.n_frames;
+        // the warp's two 32 x 32 staging pieces: rows of 128 bytes = 32 frames of one channel, 16-byte chunks XOR-swizzled by
+        // the row (CU_TENSOR_MAP_SWIZZLE_128B), so that the 8 lanes of a store phase hit 8 different chunks
+        const uint32_t piece_base = smem_u32(smem_raw + kStemOutOffset + warp * 2 * kStemPieceBytes) + lane * 128;
+        const uint32_t swizzle = (lane & 7) << 4;
+        const int row0 = slice * kStemN + (warp & 3) * 32;       // + clip * n_state: the piece's first row of out viewed as [batch * n_state, n_frames]
+        int pieces_out = 0;
+        TileWalk w = first;
+        if (buf) w.advance(step);
+        for (int k = buf; k < my_tiles; k += 2, w.advance(step), w.advance(step)) {
+            const int t0 = w.tile * kStemTile;
+            float* out = out_n + (static_cast<int64_t>(w.clip) * a.n_state * a.n_frames + t0);
+            mbar_wait_relaxed(&bars.d_full[buf], parity, 100);
             parity ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -329,12 +386,25 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
 #pragma unroll
                 for (int i = 0; i < 32; ++i) d[i] = gelu_from_half(fmaf(d[i], 0.5f, half_bias));
                 const int t = t0 + piece * 32;
+                if (t >= a.n_frames) continue;                    // (warp-uniform)
                 if (a.vector_io) {
+                    // the staging piece used two stores ago must have been read by the TMA unit
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    const uint32_t dst = piece_base + (pieces_out & 1) * kStemPieceBytes;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8)
-                        if (t + i < a.n_frames)   // (n_frames % 8 == 0: a group of 8 is inside or outside as a whole)
-                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + piece * 32 + i), "f"(d[i]), "f"(d[i + 1]),
-                                         "f"(d[i + 2]), "f"(d[i + 3]), "f"(d[i + 4]), "f"(d[i + 5]), "f"(d[i + 6]), "f"(d[i + 7]) : "memory");
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j << 4) ^ swizzle)), "f"(d[4 * j]), "f"(d[4 * j + 1]),
+                                     "f"(d[4 * j + 2]), "f"(d[4 * j + 3]) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        // frames beyond n_frames are clipped by the tensor map
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&out_map), "r"(t), "r"(w.clip * a.n_state + row0), "r"(dst - lane * 128) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++pieces_out;
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
@@ -342,6 +412,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                 }
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staging pieces live until the stores have read them
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -369,10 +440,34 @@ cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, c
     int64_t walkers = sms / slices;                                   // CTAs per slice; every CTA of the grid is resident
     if (walkers < 1) walkers = 1;
     if (walkers > tiles) walkers = tiles;
-    const int vector_io = n_frames % 8 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 32 == 0;
+    // the output as the TMA unit sees it: [batch * n_state rows, n_frames], boxes of 32 rows x 32 frames, 128-byte swizzle.
+    // Anything that keeps it from being described (odd n_frames, unaligned pointers, an absurd size) leaves vector_io = 0:
+    // scalar loads and stores.
+    CUtensorMap out_map;
+    std::memset(&out_map, 0, sizeof(out_map));
+    int vector_io = 0;
+    if (n_frames % 4 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+        batch * n_state < (int64_t{1} << 31)) {
+        using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = [] {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+            return reinterpret_cast<EncodeFn>(fn);
+        }();
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(n_frames), static_cast<cuuint64_t>(batch * n_state)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(n_frames) * 4};
+        const cuuint32_t box[2] = {32, 32};
+        const cuuint32_t elem[2] = {1, 1};
+        if (encode != nullptr && encode(&out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            vector_io = 1;
+    }
     StemArgs a{mel, max_keys, tile_keys, global_max, weight, bias, out, batch, n_frames, n_state, vector_io};
     ProfileScope profile(3, stream);
-    stem_conv1_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kStemThreads, kStemSmem, stream>>>(a);
+    stem_conv1_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kStemThreads, kStemSmem, stream>>>(a, out_map);
     count_launch();
     return cudaGetLastError();
 }
