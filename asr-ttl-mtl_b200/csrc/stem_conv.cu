@@ -76,6 +76,12 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         __nanosleep(sleep_ns);
     }
 }
+// a loader group's wait for its stage: one warp polls the mbarrier, the other seven block on a named barrier - a blocked
+// warp takes no issue slots, a polling one does (measured: sixteen polling warps took a third of the SM's issue slots)
+__device__ __forceinline__ void stage_wait(uint64_t* bar, uint32_t parity, bool leader, int bar_id) {
+    if (leader) mbar_wait_relaxed(bar, parity, 500);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kStemLoaderWarps * 32) : "memory");
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {      // round to nearest (ties away), as cudnn / cuBLAS do
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                         }
                     }
                 }
-                mbar_wait_relaxed(&bars.x_empty[stage], parity, 200);
+                stage_wait(&bars.x_empty[stage], parity, lw == 0, 1 + group);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     if (r < 2 || third) {
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                 }
             } else {
                 // any n_frames / alignment: element by element (consecutive threads along the frame axis)
-                mbar_wait_relaxed(&bars.x_empty[stage], parity, 200);
+                stage_wait(&bars.x_empty[stage], parity, lw == 0, 1 + group);
 #pragma unroll 1
                 for (int i = lt; i < kStemMels * kStemTile; i += kStemLoaderWarps * 32) {
                     const int c = i / kStemTile, f = i % kStemTile;
