@@ -19,6 +19,7 @@ from .audio import (  # noqa: F401
     log_mel_spectrogram,
     log_mel_spectrogram_batch,
     mel_filters,
+    mel_windows,
     pad_or_trim,
 )
 from .install import install, uninstall  # noqa: F401

@@ -330,6 +330,53 @@ def collate_log_mels(
     return log_mel_spectrogram_batch(staged, n_mels=n_mels, lengths=lens.to(dev, non_blocking=True), variant=variant)
 
 
+def mel_windows(
+    mel: torch.Tensor,
+    seeks,
+    sizes=None,
+    *,
+    window_frames: int = N_FRAMES,
+    dtype: torch.dtype = torch.float16,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Cut decoding windows out of one utterance's log-mel spectrogram in ONE launch.
+
+    Equals ``torch.stack([pad_or_trim(mel[:, s : s + n], window_frames).to(dtype) for s, n in zip(seeks, sizes)])`` - the
+    ``mel_segment`` of whisper/transcribe.py:282-286 (and :150 with ``seeks=[0]``) for many windows at once, written
+    straight into zero-padded ``[n_windows, n_mels, window_frames]`` windows in float32 or float16.  ``mel`` is the
+    ``[n_mels, T]`` float32 CUDA tensor ``log_mel_spectrogram(audio, padding=N_SAMPLES)`` returned; ``seeks`` (and the
+    optional ``sizes``, default: whole windows) are sequences or int32 tensors of window starts / kept frames.
+    """
+    _require_cuda()
+    if not torch.is_tensor(mel) or mel.dim() != 2 or mel.dtype != torch.float32 or not mel.is_cuda:
+        raise RuntimeError("mel_windows: expected a 2D float32 CUDA log-mel spectrogram [n_mels, T]")
+    if dtype not in (torch.float32, torch.float16):
+        raise ValueError(f"dtype must be torch.float32 or torch.float16, got {dtype}")
+    mel = mel.detach().contiguous()
+    n_mels, n_frames = mel.shape
+    with torch.cuda.device(mel.device):
+        seeks_t = torch.as_tensor(seeks).to(device=mel.device, dtype=torch.int32).contiguous().reshape(-1)
+        n_windows = int(seeks_t.shape[0])
+        sizes_t = None
+        if sizes is not None:
+            sizes_t = torch.as_tensor(sizes).to(device=mel.device, dtype=torch.int32).contiguous().reshape(-1)
+            if sizes_t.shape != seeks_t.shape:
+                raise ValueError("sizes must have as many entries as seeks")
+        shape = (n_windows, n_mels, int(window_frames))
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=mel.device)
+        elif out.shape != shape or out.dtype != dtype or out.device != mel.device or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous {dtype} {shape} tensor on {mel.device}")
+        stream = torch.cuda.current_stream(mel.device)
+        _native.check(_native.load().b200mel_mel_windows_device(
+            mel.data_ptr(), n_mels, n_frames, seeks_t.data_ptr(), sizes_t.data_ptr() if sizes_t is not None else None,
+            n_windows, int(window_frames), out.data_ptr(), _native.FLAG_OUT_F16 if dtype == torch.float16 else 0, stream.cuda_stream))
+        for t in (mel, seeks_t, sizes_t):
+            if t is not None:
+                t.record_stream(stream)
+    return out
+
+
 def gpu_launches() -> int:
     """Kernels launched by libb200mel.so in this process (bench.py's ``gpu_launches``)."""
     return _native.launch_count()

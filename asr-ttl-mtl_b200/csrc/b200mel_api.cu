@@ -320,6 +320,17 @@ int b200mel_stem_conv1_gelu_device(const float* mel, const void* workspace, unsi
     return B200MEL_OK;
 }
 
+int b200mel_mel_windows_device(const float* mel, int n_mels, int64_t n_frames, const int32_t* seeks, const int32_t* sizes,
+                               int n_windows, int window_frames, void* out, unsigned flags, void* stream) {
+    if (n_windows < 0 || n_mels < 0 || n_frames < 0 || window_frames < 0 || n_mels > 65535 || n_windows > 65535) return B200MEL_ERR_BAD_ARGUMENT;
+    if (flags & ~B200MEL_FLAG_OUT_F16) return B200MEL_ERR_BAD_ARGUMENT;
+    if (n_windows == 0 || n_mels == 0 || window_frames == 0) return B200MEL_OK;
+    if (mel == nullptr || seeks == nullptr || out == nullptr) return B200MEL_ERR_NULL_POINTER;
+    B200_CUDA(launch_mel_windows(mel, n_mels, n_frames, seeks, sizes, n_windows, window_frames, out, (flags & B200MEL_FLAG_OUT_F16) ? 1 : 0,
+                                 static_cast<cudaStream_t>(stream)));
+    return B200MEL_OK;
+}
+
 int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int dtype, int64_t batch,
                         int64_t n_samples, int64_t stride_b, const int32_t* lengths_host,
                         int64_t right_zero_pad, float* out_host, unsigned flags, int variant) {
@@ -335,6 +346,9 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
     if (batch > 1 && stride_b < n_samples) return B200MEL_ERR_BAD_ARGUMENT;
 
     std::lock_guard<std::mutex> lock(plan->host_mutex);
+    // the caller's current device is restored on every way out
+    int caller_device = -1;
+    B200_CUDA(cudaGetDevice(&caller_device));
     B200_CUDA(cudaSetDevice(plan->device));
     const size_t in_elem = dtype == B200MEL_F32 ? sizeof(float) : sizeof(int16_t);
     const int64_t elems_per_clip = static_cast<int64_t>(plan->n_mels) * n_frames;
@@ -350,11 +364,9 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
     if (chunk > batch) chunk = batch;
     const int slots = global_max ? 1 : kHostSlots;
 
-    int result = B200MEL_OK;
-    int64_t issued = 0;
-    for (int64_t c0 = 0; c0 < batch && result == B200MEL_OK; c0 += chunk, ++issued) {
-        HostSlot& s = plan->slots[issued % slots];
-        const int64_t n = (batch - c0 < chunk) ? batch - c0 : chunk;
+    // one chunk: copy in, compute, copy out - all on the slot's stream.  A failure returns its status; the caller of this
+    // lambda stops issuing and still drains every slot, so no copy is in flight into the caller's buffers on return.
+    auto run_chunk = [&](HostSlot& s, int64_t c0, int64_t n) -> int {
         if (s.stream == nullptr) B200_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         // the slot's previous chunk must have drained before its buffers are reused / regrown
         B200_CUDA(cudaStreamSynchronize(s.stream));
@@ -375,18 +387,28 @@ int b200mel_logmel_host(const b200mel_plan* plan_c, const void* audio_host, int 
                                       cudaMemcpyHostToDevice, s.stream));
             d_len = s.d_len;
         }
-        result = b200mel_logmel_device(plan, s.d_in, dtype, n, n_samples, n_samples, d_len, right_zero_pad, s.d_out,
-                                       s.d_ws, flags | B200MEL_FLAG_TILE_KEYS, variant, s.stream);
-        if (result != B200MEL_OK) break;
+        const int st = b200mel_logmel_device(plan, s.d_in, dtype, n, n_samples, n_samples, d_len, right_zero_pad, s.d_out,
+                                             s.d_ws, flags | B200MEL_FLAG_TILE_KEYS, variant, s.stream);
+        if (st != B200MEL_OK) return st;
         B200_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(out_host) + static_cast<size_t>(c0) * elems_per_clip * out_elem, s.d_out,
                                   static_cast<size_t>(n) * elems_per_clip * out_elem,
                                   cudaMemcpyDeviceToHost, s.stream));
-    }
+        return B200MEL_OK;
+    };
+
+    int result = B200MEL_OK;
+    int64_t issued = 0;
+    for (int64_t c0 = 0; c0 < batch && result == B200MEL_OK; c0 += chunk, ++issued)
+        result = run_chunk(plan->slots[issued % slots], c0, (batch - c0 < chunk) ? batch - c0 : chunk);
     for (int i = 0; i < kHostSlots; ++i)
         if (plan->slots[i].stream) {
             cudaError_t e = cudaStreamSynchronize(plan->slots[i].stream);
             if (e != cudaSuccess && result == B200MEL_OK) result = cuda_fail(e, "cudaStreamSynchronize");
         }
+    if (caller_device >= 0 && caller_device != plan->device) {
+        cudaError_t e = cudaSetDevice(caller_device);
+        if (e != cudaSuccess && result == B200MEL_OK) result = cuda_fail(e, "cudaSetDevice");
+    }
     return result;
 }
 

@@ -57,6 +57,11 @@ cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch
 cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, const uint32_t* tile_keys, int global_max, int64_t batch,
                                    int n_frames, const float* weight, const float* bias, int n_state, float* out, cudaStream_t stream);
 
+// Window cut behind the front-end (mel_windows.cu): out[w, m, j] = mel[m, seeks[w] + j] for j < sizes[w] (nullptr: the whole
+// window), zeros behind - transcribe.py:282-286 for n_windows windows at once, float32 or half.
+cudaError_t launch_mel_windows(const float* mel, int n_mels, int64_t n_frames, const int32_t* seeks, const int32_t* sizes, int n_windows,
+                               int window_frames, void* out, int out_f16, cudaStream_t stream);
+
 uint64_t launches_so_far();
 void count_launch(unsigned n = 1);
 

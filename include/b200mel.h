@@ -111,8 +111,9 @@ size_t b200mel_workspace_bytes_tiles(int64_t batch, int64_t n_frames);
  *              B200MEL_FLAG_OUT_F16; the pointer is passed through the same parameter)
  *   workspace  device scratch of b200mel_workspace_bytes(batch), or of b200mel_workspace_bytes_tiles(batch, T)
  *              together with B200MEL_FLAG_TILE_KEYS
- * One launch when every utterance has its own max and at most 64 x 128 frames (the kernel normalises an utterance as soon
- * as its last tile is done, while its values are still in L2); otherwise a second, clamp-only pass follows.
+ * tcgen05 variant: the front-end kernel plus a finish kernel right behind it on the same stream (a few words per tile; it
+ * re-touches only the tiles the clamp at max - 8 changes).  FFT variant: one launch when every utterance has its own max
+ * and at most 1024 x 32 frames, otherwise a second, clamp-only pass follows.
  */
 int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype, int64_t batch,
                           int64_t n_samples, int64_t stride_b, const int32_t* lengths,
@@ -138,6 +139,19 @@ int b200mel_normalise_device(float* out, const void* workspace, int64_t batch, i
 int b200mel_stem_conv1_gelu_device(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels,
                                    int64_t n_frames, const float* weight, const float* bias, int n_state, float* out,
                                    void* stream);
+
+/* The window cut of the decoding loop, transcribe.py:282-286 (and :150 with seek 0):
+ *   mel_segment = pad_or_trim(mel[:, seek : seek + segment_size], N_FRAMES).to(device).to(dtype)
+ * for n_windows windows of one long utterance in ONE launch, written straight into zero-padded windows.
+ *   mel        device float32 [n_mels, n_frames] (the utterance's finished log-mel spectrogram)
+ *   seeks      device int32 [n_windows]: first frame of each window, >= 0
+ *   sizes      device int32 [n_windows] or NULL: frames kept of each window (segment_size; NULL = window_frames);
+ *              clipped to window_frames and to the end of `mel` like the Python slice
+ *   out        device [n_windows, n_mels, window_frames], float32, or IEEE half with B200MEL_FLAG_OUT_F16 (the rounding of
+ *              .to(torch.float16)); the frames behind a window's size are zeros
+ * n_windows, n_mels <= 65535. */
+int b200mel_mel_windows_device(const float* mel, int n_mels, int64_t n_frames, const int32_t* seeks, const int32_t* sizes,
+                               int n_windows, int window_frames, void* out, unsigned flags, void* stream);
 
 /* Host-buffer entry point (what a CPU-tensor caller of log_mel_spectrogram hits, audio.py:138-144):
  * audio_host / out_host are HOST pointers (pinned for full speed).  Copies in, computes and copies

@@ -256,6 +256,55 @@ def test_transcribe_call_pattern(b200):
     assert tuple(seg.shape) == (80, 3000) and seg.device.type == "cuda"
 
 
+def test_mel_windows_equal_the_decoding_loop_cuts(b200):
+    # transcribe.py:282-286: mel_segment = pad_or_trim(mel[:, seek : seek + segment_size], N_FRAMES).to(device).to(dtype),
+    # every window of the decoding loop in one launch, float16 (what the fp16 model gets) and float32
+    x = signals.make_signal("chirp", 16000 * 95 + 77, 3)
+    mel = b200.log_mel_spectrogram(x, 80, padding=b200.N_SAMPLES, device=DEV)
+    content_frames = mel.shape[-1] - b200.N_FRAMES
+    seeks = [0, 1, 2999, 3000, 4321, 6001, content_frames - 1234, content_frames - 1, mel.shape[-1] - 10]
+    sizes = [min(b200.N_FRAMES, max(content_frames - s, 0)) if i % 2 == 0 else b200.N_FRAMES for i, s in enumerate(seeks)]
+    for dtype in (torch.float16, torch.float32):
+        want = torch.stack([b200.pad_or_trim(mel[:, s:s + n], b200.N_FRAMES).to(dtype) for s, n in zip(seeks, sizes)])
+        got = b200.mel_windows(mel, seeks, sizes, dtype=dtype)
+        assert got.dtype == dtype and tuple(got.shape) == (len(seeks), 80, 3000)
+        assert torch.equal(got, want)
+    # whole windows by default; the language-detection window of transcribe.py:150
+    first = b200.mel_windows(mel, [0], dtype=torch.float32)
+    assert torch.equal(first[0], b200.pad_or_trim(mel, b200.N_FRAMES))
+    # a window size that is not a multiple of four and an output the vector path cannot take
+    odd = b200.mel_windows(mel, [5, 17], [101, 7], window_frames=1001, dtype=torch.float16)
+    want = torch.stack([b200.pad_or_trim(mel[:, 5:106], 1001), b200.pad_or_trim(mel[:, 17:24], 1001)]).half()
+    assert torch.equal(odd, want)
+    assert b200.mel_windows(mel, [], dtype=torch.float16).shape == (0, 80, 3000)
+    with pytest.raises(RuntimeError):
+        b200.mel_windows(mel.cpu(), [0])
+
+
+def test_front_end_next_to_a_kernel_that_holds_the_sms(b200):
+    # the trainer's situation: the front-end is launched while another stream keeps the SMs busy (here: a chain of large
+    # matmuls), so only some of its CTAs are resident at a time.  No CTA waits for another one, so it must finish with
+    # the same bits as a launch on an idle GPU.
+    x = torch.from_numpy(np.stack([signals.make_signal("gauss", 480000, 300 + i) for i in range(24)])).to(DEV)
+    x[5, 200000:] = 0.0                                         # one clip with a zero tail: the finish kernel's clamp path
+    want = b200.log_mel_spectrogram_batch(x)
+    torch.cuda.synchronize()
+    a = torch.randn(8192, 8192, device=DEV, dtype=torch.bfloat16)
+    side, main = torch.cuda.Stream(), torch.cuda.current_stream()
+    with torch.cuda.stream(side):
+        for _ in range(40):
+            a = (a @ a).clamp_(-1, 1)
+    got = [b200.log_mel_spectrogram_batch(x) for _ in range(6)]   # enqueued while the matmuls run
+    busy = not side.query()
+    torch.cuda.synchronize()
+    assert busy, "the side stream had already drained: the test did not overlap anything"
+    for g in got:
+        assert torch.equal(g, want)
+    from asr_ttl_mtl_b200 import _native
+    assert _native.kernel_fault() == (0, 0)
+    del main
+
+
 def test_nan_and_inf_poison_only_their_own_utterance(b200):
     x = np.stack([signals.make_signal("gauss", 16000, 20 + i) for i in range(3)])
     x[1, 777] = np.nan
