@@ -62,7 +62,7 @@ constexpr uint32_t kWaitHintNs = 20000;      // suspend-time hint of one try_wai
 constexpr int kTraceTiles = 8, kTraceEvents = 16, kTraceRoles = 6;
 constexpr int kTraceWords = kTraceRoles * kTraceTiles * kTraceEvents + 8;
 #if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
-// (bring-up switches ride in the upper bits of trace_first: 0x200 = count without the fence, 0x400 = no L2 prefetch, 0x800 = bulk instead of tensor L2 prefetch - measurement only, wrong results for out-of-range data / the clamp path)
+// (bring-up switches ride in the upper bits of trace_first: 0x400 = no L2 prefetch, 0x800 = bulk instead of tensor L2 prefetch, 0x1000 = no finish in the epilogue, 0x2000 = no mel sums, 0x4000 = never repeat the E sweep, 0x8000 = one chunk per fold warp and sweep - measurement only, wrong results)
 #define TC_DEBUG_FLAG(bit) ((trace_first_arg & (bit)) != 0)
 #else
 #define TC_DEBUG_FLAG(bit) false
@@ -673,6 +673,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
                     if (lane == 0) mbar_arrive(&bars->d_empty);   // the next unit may overwrite the accumulator
                     if (quad == 0) TC_TRACE(4, ti, 3 * u + 1);
                 }
+                if (TC_DEBUG_FLAG(0x2000)) continue;   // (measurement only: pull and release, no mel sums)
                 if ((u & 1) == 0) {
                     if (piece == 0) tc_epilogue_unit<NM, 0, 0, L::piece_cols>(d, acc);
                     else tc_epilogue_unit<NM, 0, (L::pieces - 1) * L::piece_cols, L::piece_cols>(d, acc);
@@ -685,7 +686,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
             if (u == kTcUnits - 1) {
                 // ---- finish this tile: log10 clamp, coalesced row stores (lane = frame), extremes ----
                 const int f = quad * 32 + lane, t = prev.t0 + f;
-                const bool live = t < a.n_frames && !silent;
+                const bool live = t < a.n_frames && !silent && !TC_DEBUG_FLAG(0x1000);   // (0x1000, measurement only: no finish)
                 const int64_t pitch = a.n_frames;
                 OutT* const out = reinterpret_cast<OutT*>(a.out) + prev.clip * NM * pitch + t;
                 // The affine half of the normalisation, (x + 4) / 4, is applied here (one FFMA, the same single rounding as
@@ -857,7 +858,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 // the quadrant's three warps take 5 + 4 + 4 chunks of a sweep; the O sweep hands the 5 to the other end, so
                 // that the warps come out at 9 / 8 / 9 chunks per tile
                 const int slot = sweep == 0 ? part : kFoldParts - 1 - part;
-                const int j0 = slot == 0 ? 0 : 1 + 4 * slot, j1 = 5 + 4 * slot;
+                const int j0 = slot == 0 ? 0 : 1 + 4 * slot, j1 = TC_DEBUG_FLAG(0x8000) ? j0 + 1 : 5 + 4 * slot;   // (0x8000, measurement only: one chunk per warp and sweep)
                 if (sweep == 0) {
                     // the E sweep with the previous tile's scale step, tracking the largest |sample|; the quadrant's two warps
                     // then agree on the step this tile calls for and repeat their chunks if it is another one
@@ -940,7 +941,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                     // Issue order: the two small products (lo Bh, hi Bl: 2^-11 of the result) first, the main product hi Bh
                     // last.  The tensor cores truncate the fp32 accumulator at every MMA; added in this order only the 7 main
                     // steps truncate at the result's own magnitude instead of all 20 (measured against the CPU emulator:
-                    // tools/parity_full.py).
+                    // tests/tools/parity_full.py).
                     const uint32_t a_hi = tmem + ui.a_hi, a_lo = tmem + ui.a_lo, b_hi = desc0 + ui.b_hi, b_lo = desc0 + ui.b_lo;
                     mma_f16_ts<false>(d_tmem, a_lo, b_hi);
                     mma_f16_ts<true>(d_tmem, a_hi, b_lo);

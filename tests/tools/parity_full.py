@@ -1,6 +1,6 @@
 """GPU box: parity of BOTH STFT kernels at the full BASELINE batch sizes, every clip, every value.
 
-    python tools/parity_full.py [--clips 256] [--emul 2]
+    python tests/tools/parity_full.py [--clips 256] [--emul 2]
 
 For configs 2 / 3 (256 x 30 s of 0.1 randn, 80 / 128 mel) prints the worst |gpu - ref|, |gpu - f64| and |ref - f64| over
 all values, how many values are more than 1e-4 from the reference, and - for the clips where the tcgen05 kernel is
@@ -17,7 +17,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import asr_ttl_mtl_b200 as b  # noqa: E402
 from oracle import logmel_oracle as orc  # noqa: E402
@@ -58,6 +58,22 @@ def main():
               f"({time.time() - t0:.0f} s)")
         e_ref = np.abs(ref - f64)
         print(f"   |ref - f64|      max {e_ref.max():.3e}   values > 5e-5: {(e_ref > 5e-5).sum()}")
+        # the reference's OWN operator sequence (audio.py:146-156) run on the GPU (torch.stft -> cuFFT, matmul -> cuBLAS,
+        # fp32 without TF32) against its CPU run: what two fp32 evaluations of the same formulas differ by at this size
+        filt = torch.from_numpy(orc.reference_filters(n_mels)).cuda()
+        win = torch.hann_window(orc.N_FFT, device="cuda")
+        saved = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        on_gpu = []
+        for row in x:
+            stft = torch.stft(row, orc.N_FFT, orc.HOP_LENGTH, window=win, return_complex=True)
+            ls = torch.clamp(filt @ (stft[..., :-1].abs() ** 2), min=1e-10).log10()
+            on_gpu.append(((torch.maximum(ls, ls.max() - 8.0) + 4.0) / 4.0).cpu().numpy())
+        torch.backends.cuda.matmul.allow_tf32 = saved
+        on_gpu = np.stack(on_gpu)
+        d_self = np.abs(on_gpu - ref)
+        print(f"   reference operators on cuda vs on cpu: |ref_cuda - ref_cpu| max {d_self.max():.3e} (> 1e-4: {(d_self > 1e-4).sum()} values)   "
+              f"|ref_cuda - f64| max {np.abs(on_gpu - f64).max():.3e}")
         for v in ("tcgen05", "fft"):
             d_ref, d_f64 = np.abs(got[v] - ref), np.abs(got[v] - f64)
             closer = (d_f64 <= e_ref + 2.5e-5)

@@ -2,7 +2,7 @@
 is each from the float64 oracle and from the fp32 reference port there?"""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import asr_ttl_mtl_b200 as b
 from oracle import logmel_oracle as orc
 
