@@ -53,6 +53,7 @@ namespace {
 constexpr int kFoldParts = 3;                 // fold warps per lane quadrant
 constexpr int kWarpEpi0 = 4 * kFoldParts, kWarpMma = kWarpEpi0 + 4;   // fold 0-11, epilogue 12-15, MMA 16 (17-19 complete the warpgroup and idle)
 constexpr int kTcWarps = 20;
+constexpr int kTcFixedPitch = 3000;          // N_FRAMES of a 30 s clip (audio.py:21): the kernels specialised for this output pitch
 constexpr int kTcThreads = kTcWarps * 32;   // 640
 constexpr uint32_t kSpinLimit = 1u << 17;    // x 20 us hint = 2.6 s: a protocol bug ends the kernel instead of hanging the device
 constexpr uint32_t kWaitHintNs = 20000;      // suspend-time hint of one try_wait
@@ -623,7 +624,7 @@ static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) =
               tc_left_col(1) - tc_left_col(0) == 6 && tc_left_col(3) - tc_left_col(2) == 6, "column arithmetic of sweep_store");
 
 // ---- epilogue ---------------------------------------------------------------------------------------
-template <int NM, typename OutT>
+template <int NM, typename OutT, int PITCH>
 __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* trace, const int trace_first_arg, TcBarriers* bars,
                                               const TcTileInfo* info, TcAbort ab,
                                               uint32_t tmem, int quad, int lane, int64_t total_tiles, int tiles_per_clip) {
@@ -645,7 +646,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
         const int ti = static_cast<int>(k);
         prev = cursor.at;
         cursor.advance();
-        float unscale = 1.0f;
+        float y_offset = 1.0f;
         bool silent = false;
 #pragma unroll 1
         for (int u = 0; u < kTcUnits; ++u) {
@@ -655,7 +656,7 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
             tc_fence_after();
             if (u == 0) {
                 // the quadrant's scale step was written before the folds released the E operand, i.e. before this unit's MMAs
-                unscale = c_fold.unscale[*reinterpret_cast<const volatile uint32_t*>(&info->scale[k & 1][quad])];
+                y_offset = c_fold.y_offset[*reinterpret_cast<const volatile uint32_t*>(&info->scale[k & 1][quad])];
                 // a tile whose samples are ALL zero (zero padding) is not stored: the finish kernel fills it (it needs per-tile keys for that)
                 const volatile uint32_t* z = info->silent[k & 1];
                 silent = a.tile_keys != nullptr && (z[0] & z[1] & z[2] & z[3]) != 0u;
@@ -689,28 +690,37 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
                 const bool live = t < a.n_frames && !silent && !TC_DEBUG_FLAG(0x1000);   // (0x1000, measurement only: no finish)
                 const int64_t pitch = a.n_frames;
                 OutT* const out = reinterpret_cast<OutT*>(a.out) + prev.clip * NM * pitch + t;
-                // The affine half of the normalisation, (x + 4) / 4, is applied here (one FFMA, the same single rounding as
-                // audio.py:156); only the clamp at max - 8 is left for the finish kernel - which skips the tile when its
-                // smallest value is not below max - 8 (tracked here as well).
+                // y = (log10(max(P, 1e-10)) + 4) / 4 of the mel power P = acc 2^-2k, as ONE fused multiply-add behind the MUFU:
+                //   y = log2(acc) (log10(2) / 4) + (1 - 2k log10(2) / 4),  then max(y, -1.5)   [-1.5 = (log10(1e-10) + 4) / 4]
+                // (the data scale leaves as part of the addend - exact in real arithmetic, a power of two; the clamp at 1e-10
+                // moves behind the logarithm, where log2(0) = -inf comes out as exactly -1.5, like the reference's clamp).
+                // Only the clamp at max - 8 is left for the finish kernel - which skips the tile when its smallest value is not
+                // below max - 8 (tracked here as well, in y; converted to log10 units once per lane).
                 float mx = __uint_as_float(0xff800000u), mn = __uint_as_float(0x7f800000u);
                 if (live) {
-                    constexpr float scale = 0.25f, shift = 1.0f;
-                    const uint32_t pitch32 = static_cast<uint32_t>(a.n_frames);
-                    // two mels per step: the data scale out of the power (exact: a power of two), log2 on the MUFU, then
-                    // log10 scaling and the affine map as packed FMUL2 / FFMA2 (the same two roundings per value as the scalar form)
-                    constexpr float kLog10Of2 = 0.30102999566398120f;
-                    const float2 scale2 = make_float2(scale, scale), shift2 = make_float2(shift, shift), unscale2 = make_float2(unscale, unscale);
+                    constexpr float kLog10Of2Quarter = 0.30102999566398120f * 0.25f;
+                    const float2 mul2 = make_float2(kLog10Of2Quarter, kLog10Of2Quarter), add2 = make_float2(y_offset, y_offset);
 #pragma unroll
                     for (int m = 0; m < NM; m += 2) {
-                        const float2 s = __fmul2_rn(make_float2(acc[m], acc[m + 1]), unscale2);
-                        const float2 l2 = make_float2(log2_clamped(s.x), log2_clamped(s.y));
-                        const float2 lg = __fmul2_rn(l2, make_float2(kLog10Of2, kLog10Of2));
-                        const float2 y = __ffma2_rn(lg, scale2, shift2);
-                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m), y.x);
-                        out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1), y.y);
-                        mx = max_nan(mx, max_nan(lg.x, lg.y));
-                        mn = fminf(mn, fminf(lg.x, lg.y));
+                        float2 l2;
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.x) : "f"(acc[m]));
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.y) : "f"(acc[m + 1]));
+                        float2 y = __ffma2_rn(l2, mul2, add2);
+                        y.x = max_nan(y.x, -1.5f);
+                        y.y = max_nan(y.y, -1.5f);
+                        if constexpr (PITCH > 0) {
+                            out_store(out + PITCH * m, y.x);
+                            out_store(out + PITCH * (m + 1), y.y);
+                        } else {
+                            const uint32_t pitch32 = static_cast<uint32_t>(a.n_frames);
+                            out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m), y.x);
+                            out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1), y.y);
+                        }
+                        mx = max_nan(mx, max_nan(y.x, y.y));
+                        mn = fminf(mn, fminf(y.x, y.y));
                     }
+                    mx = fmaf(mx, 4.0f, -4.0f);     // back to log10 units: what the keys hold
+                    mn = fmaf(mn, 4.0f, -4.0f);
                 }
 #pragma unroll
                 for (int i = 0; i < NM; ++i) acc[i] = 0.f;
@@ -734,7 +744,9 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
     }
 }
 
-template <typename InT, int NM, typename OutT>
+// PITCH: the output's row pitch n_frames as a compile-time constant (3000: the 30 s clips of every consumer - the row
+// stores then take immediate offsets instead of a 64-bit multiply-add each), or 0: any
+template <typename InT, int NM, typename OutT, int PITCH>
 __global__ void __launch_bounds__(kTcThreads, 1)
 logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ CUtensorMap audio_map, const int tma_rows,
                  const unsigned char* __restrict__ operands, long long* __restrict__ trace, const int trace_first_arg) {
@@ -915,7 +927,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     } else if (warp < kWarpMma) {
         // ===== epilogue warps =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-        epilogue_role<NM, OutT>(a, trace, trace_first_arg, &bars, &info, ab, tmem, quad, lane, total_tiles, tiles_per_clip);
+        epilogue_role<NM, OutT, PITCH>(a, trace, trace_first_arg, &bars, &info, ab, tmem, quad, lane, total_tiles, tiles_per_clip);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == kWarpMma) {
@@ -979,9 +991,10 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     if (err != cudaSuccess) return err;
     if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
     if (sms_by_device[device] == 0) {
-        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (err != cudaSuccess) return err;
-        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, __half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, float, kTcFixedPitch>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(logmel_tc_kernel<InT, NM, __half, kTcFixedPitch>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (err != cudaSuccess) return err;
         int sms = 0;
         if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return err;
@@ -1035,10 +1048,14 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
 #if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
     if (std::getenv("B200MEL_TC_FLAGS") != nullptr) trace_first |= std::atoi(std::getenv("B200MEL_TC_FLAGS")) << 8;
 #endif
-    if (a.out_f16)
-        logmel_tc_kernel<InT, NM, __half><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, trace, trace_first);
-    else
-        logmel_tc_kernel<InT, NM, float><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, trace, trace_first);
+    const bool fixed = a.n_frames == kTcFixedPitch;
+    if (a.out_f16) {
+        if (fixed) logmel_tc_kernel<InT, NM, __half, kTcFixedPitch><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, trace, trace_first);
+        else logmel_tc_kernel<InT, NM, __half, 0><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, trace, trace_first);
+    } else {
+        if (fixed) logmel_tc_kernel<InT, NM, float, kTcFixedPitch><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, trace, trace_first);
+        else logmel_tc_kernel<InT, NM, float, 0><<<grid, kTcThreads, kSmemBytes, stream>>>(a, audio_map, tma_rows, tables->operands, trace, trace_first);
+    }
     count_launch();
     err = cudaGetLastError();
 #if defined(B200MEL_TC_TRACE)

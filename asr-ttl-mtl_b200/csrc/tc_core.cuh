@@ -195,6 +195,7 @@ struct TcFoldTables {
     TcFoldWeights w[kTcScales][2][kTcChunks];
     float sign[2];
     float unscale[kTcScales];   // 2^-2k
+    float y_offset[kTcScales];  // 1 - 2k log10(2) / 4: the data scale leaves as an addend of the (log10 + 4) / 4 map
     int pad[2];
 };
 constexpr int tc_clamp_sample(int n) { return n < 0 ? 0 : (n > 396 ? 396 : n); }   // group start kept inside the frame
@@ -227,6 +228,8 @@ constexpr TcFoldTables tc_make_fold_tables() {
         t.sign[sweep] = sweep == 0 ? 1.0f : -1.0f;
     }
     for (int s = 0; s < kTcScales; ++s) t.unscale[s] = tc_make_unscale().v[s];
+    for (int s = 0; s < kTcScales; ++s)
+        t.y_offset[s] = static_cast<float>(1.0 - 2.0 * tc_scale_exponent(s) * 0.30102999566398119521 / 4.0);
     t.pad[0] = t.pad[1] = 0;
     return t;
 }
