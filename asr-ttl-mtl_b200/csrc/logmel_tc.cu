@@ -498,8 +498,12 @@ __device__ __forceinline__ void expand_pcm_half(float* s_half, int pt, int bar_i
             float v[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                v[2 * j] = static_cast<float>(static_cast<int16_t>(w[j] & 0xffffu)) * (1.0f / 32768.0f);
-                v[2 * j + 1] = static_cast<float>(static_cast<int16_t>(w[j] >> 16)) * (1.0f / 32768.0f);
+                // int16 s -> s / 32768 without the conversion unit (I2F is 8 issue cycles a warp): with the sign bit flipped
+                // the sample is u = s + 32768 in 0..65535; the float whose bits are 0x4B00uuuu is 2^23 + u exactly, and
+                // (2^23 + u) 2^-15 - 257 = s / 32768 - exact, one fused multiply-add (audio.py:62's arithmetic)
+                const uint32_t biased = w[j] ^ 0x80008000u;
+                v[2 * j] = fmaf(__uint_as_float(__byte_perm(biased, 0x4b000000u, 0x7610)), 1.0f / 32768.0f, -257.0f);
+                v[2 * j + 1] = fmaf(__uint_as_float(__byte_perm(biased, 0x4b000000u, 0x7632)), 1.0f / 32768.0f, -257.0f);
             }
             float4* dst = reinterpret_cast<float4*>(s_half + rr * kTcRowPitch + col);
             dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -624,6 +628,68 @@ static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) =
               tc_left_col(1) - tc_left_col(0) == 6 && tc_left_col(3) - tc_left_col(2) == 6, "column arithmetic of sweep_store");
 
 // ---- epilogue ---------------------------------------------------------------------------------------
+// ---- finish a tile: log10 clamp, coalesced row stores (lane = frame), extremes; leaves acc zeroed ----
+// `at`: the tile; k: its index among the CTA's tiles; y_offset / silent: what the folds said about it (see epilogue_role)
+template <int NM, typename OutT, int PITCH>
+__device__ __forceinline__ void epilogue_finish_tile(const LogmelArgs& a, long long* trace, const int trace_first_arg, float (&acc)[NM],
+                                                     const TileCoord& at, int64_t k, float y_offset, bool silent, int quad, int lane) {
+    [[maybe_unused]] const int trace_first = trace_first_arg & 0xff;
+    [[maybe_unused]] const int ti = static_cast<int>(k);
+    const int f = quad * 32 + lane, t = at.t0 + f;
+    const bool live = t < a.n_frames && !silent && !TC_DEBUG_FLAG(0x1000);   // (0x1000, measurement only: no finish)
+    const int64_t pitch = a.n_frames;
+    OutT* const out = reinterpret_cast<OutT*>(a.out) + at.clip * NM * pitch + t;
+    // y = (log10(max(P, 1e-10)) + 4) / 4 of the mel power P = acc 2^-2k, as ONE fused multiply-add behind the MUFU:
+    //   y = log2(acc) (log10(2) / 4) + (1 - 2k log10(2) / 4),  then max(y, -1.5)   [-1.5 = (log10(1e-10) + 4) / 4]
+    // (the data scale leaves as part of the addend - exact in real arithmetic, a power of two; the clamp at 1e-10
+    // moves behind the logarithm, where log2(0) = -inf comes out as exactly -1.5, like the reference's clamp).
+    // Only the clamp at max - 8 is left for the finish kernel - which skips the tile when its smallest value is not
+    // below max - 8 (tracked here as well, in y; converted to log10 units once per lane).
+    float mx = __uint_as_float(0xff800000u), mn = __uint_as_float(0x7f800000u);
+    if (live) {
+        constexpr float kLog10Of2Quarter = 0.30102999566398120f * 0.25f;
+        const float2 mul2 = make_float2(kLog10Of2Quarter, kLog10Of2Quarter), add2 = make_float2(y_offset, y_offset);
+#pragma unroll
+        for (int m = 0; m < NM; m += 2) {
+            float2 l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.x) : "f"(acc[m]));
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.y) : "f"(acc[m + 1]));
+            float2 y = __ffma2_rn(l2, mul2, add2);
+            y.x = max_nan(y.x, -1.5f);
+            y.y = max_nan(y.y, -1.5f);
+            if constexpr (PITCH > 0) {
+                out_store(out + PITCH * m, y.x);
+                out_store(out + PITCH * (m + 1), y.y);
+            } else {
+                const uint32_t pitch32 = static_cast<uint32_t>(a.n_frames);
+                out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m), y.x);
+                out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1), y.y);
+            }
+            mx = max_nan(mx, max_nan(y.x, y.y));
+            mn = fminf(mn, fminf(y.x, y.y));
+        }
+        mx = fmaf(mx, 4.0f, -4.0f);     // back to log10 units: what the keys hold
+        mn = fmaf(mn, 4.0f, -4.0f);
+    }
+#pragma unroll
+    for (int i = 0; i < NM; ++i) acc[i] = 0.f;
+    if (quad == 0) TC_TRACE(4, ti, 15);
+    uint32_t key = live ? max_key_encode(mx) : 0u;
+    key = __reduce_max_sync(0xffffffffu, key);
+    uint32_t inv = live ? ~max_key_encode(mn) : 0u;
+    inv = __reduce_max_sync(0xffffffffu, inv);
+    if (lane == 0 && key != 0u) {       // (key 0: nothing stored - frames past the end, or a silent tile)
+        atomicMax(a.max_keys + (a.global_max ? 0 : at.clip), key);
+        atomicMax(a.min_keys + at.clip, inv);
+        if (a.tile_keys != nullptr) {   // the tile's own extremes: lets the finish kernel skip or fill whole tiles
+            uint32_t* tk = a.tile_keys + 2 * (static_cast<int64_t>(blockIdx.x) + k * gridDim.x);
+            atomicMax(tk, key);
+            atomicMax(tk + 1, inv);
+        }
+    }
+    if (quad == 0) TC_TRACE(4, ti, 12);
+}
+
 template <int NM, typename OutT, int PITCH>
 __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* trace, const int trace_first_arg, TcBarriers* bars,
                                               const TcTileInfo* info, TcAbort ab,
@@ -636,15 +702,21 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
     const uint32_t d_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kTcDCol;
     uint32_t d_parity = 0;
     const int64_t my_tiles = static_cast<int64_t>(blockIdx.x) < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    TileCoord prev{0, 0};
     TileCursor cursor(tiles_per_clip);
-    // Unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep).  A tile is FINISHED (log10, stores, extremes) right
-    // after its last unit: the tensor cores then wait for the next tile's E operand anyway, and unit 0 of the next tile
-    // runs while the stores go out.
+    // Unit order on the tensor cores: 0, 1 (E sweep), 2, 3 (O sweep).  The accumulator is single: the tensor cores start a
+    // unit only when the previous one has been pulled into registers.  So a tile is FINISHED (log10, stores, extremes)
+    //   - 80 mels (the unit's 104 columns fit the registers beside the 80 sums): after unit 0 of the NEXT tile has been
+    //     pulled - the accumulator is free again while the stores go out, unit 1's MMAs (and with them the release of the
+    //     E operand to the folds) do not wait for the finish;
+    //   - 128 mels (the columns come in two pieces): right after the tile's last unit.
+    constexpr bool kDeferFinish = L::pieces == 1;
+    TileCoord done{0, 0};
+    float y_done = 1.0f;
+    bool silent_done = false;
 #pragma unroll 1
     for (int64_t k = 0; k < my_tiles; ++k) {
         const int ti = static_cast<int>(k);
-        prev = cursor.at;
+        const TileCoord cur = cursor.at;
         cursor.advance();
         float y_offset = 1.0f;
         bool silent = false;
@@ -674,6 +746,9 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
                     if (lane == 0) mbar_arrive(&bars->d_empty);   // the next unit may overwrite the accumulator
                     if (quad == 0) TC_TRACE(4, ti, 3 * u + 1);
                 }
+                if constexpr (kDeferFinish) {
+                    if (u == 0 && k > 0) epilogue_finish_tile<NM, OutT, PITCH>(a, trace, trace_first_arg, acc, done, k - 1, y_done, silent_done, quad, lane);
+                }
                 if (TC_DEBUG_FLAG(0x2000)) continue;   // (measurement only: pull and release, no mel sums)
                 if ((u & 1) == 0) {
                     if (piece == 0) tc_epilogue_unit<NM, 0, 0, L::piece_cols>(d, acc);
@@ -684,63 +759,16 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
                 }
             }
             if (quad == 0) TC_TRACE(4, ti, 3 * u + 2);
-            if (u == kTcUnits - 1) {
-                // ---- finish this tile: log10 clamp, coalesced row stores (lane = frame), extremes ----
-                const int f = quad * 32 + lane, t = prev.t0 + f;
-                const bool live = t < a.n_frames && !silent && !TC_DEBUG_FLAG(0x1000);   // (0x1000, measurement only: no finish)
-                const int64_t pitch = a.n_frames;
-                OutT* const out = reinterpret_cast<OutT*>(a.out) + prev.clip * NM * pitch + t;
-                // y = (log10(max(P, 1e-10)) + 4) / 4 of the mel power P = acc 2^-2k, as ONE fused multiply-add behind the MUFU:
-                //   y = log2(acc) (log10(2) / 4) + (1 - 2k log10(2) / 4),  then max(y, -1.5)   [-1.5 = (log10(1e-10) + 4) / 4]
-                // (the data scale leaves as part of the addend - exact in real arithmetic, a power of two; the clamp at 1e-10
-                // moves behind the logarithm, where log2(0) = -inf comes out as exactly -1.5, like the reference's clamp).
-                // Only the clamp at max - 8 is left for the finish kernel - which skips the tile when its smallest value is not
-                // below max - 8 (tracked here as well, in y; converted to log10 units once per lane).
-                float mx = __uint_as_float(0xff800000u), mn = __uint_as_float(0x7f800000u);
-                if (live) {
-                    constexpr float kLog10Of2Quarter = 0.30102999566398120f * 0.25f;
-                    const float2 mul2 = make_float2(kLog10Of2Quarter, kLog10Of2Quarter), add2 = make_float2(y_offset, y_offset);
-#pragma unroll
-                    for (int m = 0; m < NM; m += 2) {
-                        float2 l2;
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.x) : "f"(acc[m]));
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.y) : "f"(acc[m + 1]));
-                        float2 y = __ffma2_rn(l2, mul2, add2);
-                        y.x = max_nan(y.x, -1.5f);
-                        y.y = max_nan(y.y, -1.5f);
-                        if constexpr (PITCH > 0) {
-                            out_store(out + PITCH * m, y.x);
-                            out_store(out + PITCH * (m + 1), y.y);
-                        } else {
-                            const uint32_t pitch32 = static_cast<uint32_t>(a.n_frames);
-                            out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m), y.x);
-                            out_store(out + static_cast<uint64_t>(pitch32) * static_cast<uint32_t>(m + 1), y.y);
-                        }
-                        mx = max_nan(mx, max_nan(y.x, y.y));
-                        mn = fminf(mn, fminf(y.x, y.y));
-                    }
-                    mx = fmaf(mx, 4.0f, -4.0f);     // back to log10 units: what the keys hold
-                    mn = fmaf(mn, 4.0f, -4.0f);
-                }
-#pragma unroll
-                for (int i = 0; i < NM; ++i) acc[i] = 0.f;
-                if (quad == 0) TC_TRACE(4, ti, 15);
-                uint32_t key = live ? max_key_encode(mx) : 0u;
-                key = __reduce_max_sync(0xffffffffu, key);
-                uint32_t inv = live ? ~max_key_encode(mn) : 0u;
-                inv = __reduce_max_sync(0xffffffffu, inv);
-                if (lane == 0 && key != 0u) {       // (key 0: nothing stored - frames past the end, or a silent tile)
-                    atomicMax(a.max_keys + (a.global_max ? 0 : prev.clip), key);
-                    atomicMax(a.min_keys + prev.clip, inv);
-                    if (a.tile_keys != nullptr) {   // the tile's own extremes: lets the finish kernel skip or fill whole tiles
-                        uint32_t* tk = a.tile_keys + 2 * (static_cast<int64_t>(blockIdx.x) + k * gridDim.x);
-                        atomicMax(tk, key);
-                        atomicMax(tk + 1, inv);
-                    }
-                }
-                if (quad == 0) TC_TRACE(4, ti, 12);
+            if constexpr (!kDeferFinish) {
+                if (u == kTcUnits - 1) epilogue_finish_tile<NM, OutT, PITCH>(a, trace, trace_first_arg, acc, cur, k, y_offset, silent, quad, lane);
             }
         }
+        done = cur;
+        y_done = y_offset;
+        silent_done = silent;
+    }
+    if constexpr (kDeferFinish) {
+        if (my_tiles > 0) epilogue_finish_tile<NM, OutT, PITCH>(a, trace, trace_first_arg, acc, done, my_tiles - 1, y_done, silent_done, quad, lane);
     }
 }
 
