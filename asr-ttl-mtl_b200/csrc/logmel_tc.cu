@@ -1031,7 +1031,13 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
     const int tiles_per_clip = (a.n_frames + kTcTileFrames - 1) / kTcTileFrames;
     const int64_t tiles = a.batch * tiles_per_clip;
     // one CTA per SM at most; CTAs never wait for one another, so any number of them may actually be resident
-    const unsigned grid = static_cast<unsigned>(tiles < sms_by_device[device] ? tiles : sms_by_device[device]);
+    unsigned grid = static_cast<unsigned>(tiles < sms_by_device[device] ? tiles : sms_by_device[device]);
+#if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
+    if (std::getenv("B200MEL_TC_GRID") != nullptr) {   // measurement only: fewer CTAs (what a tile costs without the other SMs' traffic)
+        const unsigned want = static_cast<unsigned>(std::atoi(std::getenv("B200MEL_TC_GRID")));
+        if (want >= 1 && want < grid) grid = want;
+    }
+#endif
     // the batch as the TMA unit sees it (see "loaders" above); any reason it cannot be described leaves tma_rows = 0
     // and every tile in cooperative mode
     CUtensorMap audio_map;
@@ -1060,6 +1066,9 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
             tma_rows = static_cast<int>(rows);
     }
+#if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
+    if (std::getenv("B200MEL_TC_NO_TMA") != nullptr) tma_rows = 0;   // measurement only: every tile staged by the fold warps (cp.async)
+#endif
     ProfileScope profile(2, stream);
     long long* trace = nullptr;
     int trace_first = 0;

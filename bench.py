@@ -243,6 +243,19 @@ def cpu_baseline(n_mels: int, seconds: float, with_cuda: bool) -> dict:
                   f"torch {torch.__version__}",
         "ms_per_clip": 1e3 * elapsed / done,
     }
+    # BASELINE config 1: ONE clip, 0.1 randn(480000) from the CPU generator with seed 0, median of 20 calls after 2 warm-ups
+    g0 = torch.Generator().manual_seed(0)
+    one = (0.1 * torch.randn(N_SAMPLES, generator=g0)).numpy()
+    for _ in range(2):
+        fn(one, n_mels)
+    laps = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        fn(one, n_mels)
+        laps.append(time.perf_counter() - t0)
+    med = statistics.median(laps)
+    out["config1"] = {"workload": "one synthetic 30 s clip, reference CPU path (BASELINE config 1)", "ms_median_of_20": 1e3 * med,
+                      "value": CLIP_SECONDS / 3600.0 / med, "unit": "audio-hours/s", "cores": threads}
     # BASELINE.md §3 run A: one thread
     torch.set_num_threads(1)
     try:
