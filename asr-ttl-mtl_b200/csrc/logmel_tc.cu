@@ -271,49 +271,53 @@ __device__ __forceinline__ void out_store4(__half* p, float4 v) {
     *reinterpret_cast<uint2*>(p) = r;
 }
 
-// one warp overwrites one tile with the clamp value (every value of the tile was below it): stores only
+// The finish kernel's blocks (8 warps) work on one tile at a time together: warp w takes mel rows w, w + 8, ...; a lane is a
+// column of four frames.  All of a warp's loads are issued before its first store, so a tile costs ONE round trip to L2 -
+// a warp walking the rows of a tile alone would pay one per row pair, and a batch in which only a few tiles need the clamp
+// (128 mels: a handful per 6144; zero-padded clips: the one tile per clip where the sound stops) would wait for it.
+constexpr int kFinishWarps = 8;
+
+// fill: every value of the tile was below the clamp (or never stored) - stores only
 template <int NM, typename OutT>
-__device__ __forceinline__ void fill_tile_tc(OutT* __restrict__ tile_out, int64_t pitch, int frames, float v, int lane) {
+__device__ __forceinline__ void fill_tile_rows(OutT* __restrict__ tile_out, int64_t pitch, int frames, float v, int warp, int lane) {
     if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & (4 * sizeof(OutT) - 1)) == 0 && (frames & 3) == 0) {
         if (lane < (frames >> 2)) {
-            OutT* p = tile_out + 4 * lane;
             const float4 v4 = make_float4(v, v, v, v);
 #pragma unroll 4
-            for (int row = 0; row < NM; ++row, p += pitch) out_store4(p, v4);
+            for (int row = warp; row < NM; row += kFinishWarps) out_store4(tile_out + row * pitch + 4 * lane, v4);
         }
     } else {
-        for (int i = lane; i < NM * frames; i += 32) out_store(tile_out + (i / frames) * pitch + i % frames, v);
+        for (int row = warp; row < NM; row += kFinishWarps)
+            for (int i = lane; i < frames; i += 32) out_store(tile_out + row * pitch + i, v);
     }
 }
 
-// one warp clamps one tile (NM rows of `frames` values at `pitch`) in place
+// clamp in place (NM rows of `frames` values at `pitch`); g: the clamp in rescaled units
 template <int NM, typename OutT>
-__device__ __forceinline__ void normalise_tile_tc(OutT* __restrict__ tile_out, int64_t pitch, int frames, float g /* the clamp in rescaled units */, int lane) {
+__device__ __forceinline__ void normalise_tile_rows(OutT* __restrict__ tile_out, int64_t pitch, int frames, float g, int warp, int lane) {
+    constexpr int kRows = NM / kFinishWarps;                                    // 10 or 16 rows per warp
+    static_assert(NM % kFinishWarps == 0, "rows per warp");
     if ((pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(tile_out) & (4 * sizeof(OutT) - 1)) == 0) {
-        // whole mel rows (lane = 4-value column), two rows in flight
         if (lane < (frames >> 2)) {
-            OutT* p = tile_out + 4 * lane;
-            int row = 0;
-#pragma unroll 1
-            for (; row + 1 < NM; row += 2, p += 2 * pitch) {
-                const float4 x0 = out_load4(p), x1 = out_load4(p + pitch);
-                out_store4(p, normalise4(x0, g));
-                out_store4(p + pitch, normalise4(x1, g));
-            }
-#pragma unroll 1
-            for (; row < NM; ++row, p += pitch) out_store4(p, normalise4(out_load4(p), g));
+            OutT* p = tile_out + warp * pitch + 4 * lane;
+            float4 x[kRows];
+#pragma unroll
+            for (int i = 0; i < kRows; ++i) x[i] = out_load4(p + i * kFinishWarps * pitch);
+#pragma unroll
+            for (int i = 0; i < kRows; ++i) out_store4(p + i * kFinishWarps * pitch, normalise4(x[i], g));
         }
         const int rest = frames & 3;                                           // 0 for whole clips (pitch % 4 == 0)
-        if (rest != 0)
-            for (int i = lane; i < NM * rest; i += 32) {
-                OutT* q = tile_out + (i / rest) * pitch + (frames & ~3) + i % rest;
+        if (rest != 0 && lane < rest)
+            for (int row = warp; row < NM; row += kFinishWarps) {
+                OutT* q = tile_out + row * pitch + (frames & ~3) + lane;
                 out_store(q, clamp_scaled(out_load(q), g));
             }
     } else {
-        for (int i = lane; i < NM * frames; i += 32) {
-            OutT* q = tile_out + (i / frames) * pitch + i % frames;
-            out_store(q, clamp_scaled(out_load(q), g));
-        }
+        for (int row = warp; row < NM; row += kFinishWarps)
+            for (int i = lane; i < frames; i += 32) {
+                OutT* q = tile_out + row * pitch + i;
+                out_store(q, clamp_scaled(out_load(q), g));
+            }
     }
 }
 
@@ -1126,40 +1130,57 @@ cudaError_t launch_tc(const LogmelArgs& a, const TcTables* tables, cudaStream_t 
 // lies wholly below the clamp - or was never stored because its samples were all zero - is filled with the constant; the
 // rest (an utterance's tile where the sound stops) is clamped value by value while it is still in L2.
 template <int NM, typename OutT>
-__global__ void __launch_bounds__(256) tc_finish_kernel(const LogmelArgs a, int tiles_per_clip) {
+__global__ void __launch_bounds__(32 * kFinishWarps) tc_finish_kernel(const LogmelArgs a, int tiles_per_clip) {
     // launched with programmatic stream serialisation: the grid is set up while the front-end kernel drains, and waits
     // here until that kernel has completed and its writes are visible
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int lane = threadIdx.x & 31;
+    struct Work { OutT* out; float value; int frames; int action; };
+    __shared__ Work work[kFinishWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t total_tiles = a.batch * tiles_per_clip;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-    for (int64_t tile = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < total_tiles; tile += stride) {
-        const int64_t clip = tile / tiles_per_clip;
-        const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kTcTileFrames;
-        const uint32_t gkey = __ldg(a.max_keys + (a.global_max ? 0 : clip));
-        const float g = gkey == 0u ? -10.0f : max_key_decode(gkey);     // (key 0: nothing but silent tiles)
-        const float floor_lg = g - 8.0f;
-        const float floor_y = ((g - 8.0f) + 4.0f) * 0.25f;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kFinishWarps;
+    // every warp looks at one tile; then the block works through the tiles that need something, all warps on each
+    for (int64_t base = static_cast<int64_t>(blockIdx.x) * kFinishWarps; base < total_tiles; base += stride) {
+        const int64_t tile = base + warp;
         int action = 0;                      // 0: leave the tile alone, 1: clamp it in place, 2: fill it
-        float fill_value = floor_y;
-        if (a.tile_keys != nullptr) {
-            const uint32_t kmax = __ldg(a.tile_keys + 2 * tile), kmin = __ldg(a.tile_keys + 2 * tile + 1);
-            if (kmax == 0u) {                // never stored: all its samples were zero, every value is log10(1e-10) = -10
-                action = 2;
-                fill_value = floor_lg > -10.0f ? floor_y : (floor_lg != floor_lg ? floor_y : -1.5f);
+        float value = 0.f;
+        int frames = 0;
+        OutT* tile_out = nullptr;
+        if (tile < total_tiles) {
+            const int64_t clip = tile / tiles_per_clip;
+            const int t0 = static_cast<int>(tile - clip * tiles_per_clip) * kTcTileFrames;
+            const uint32_t gkey = __ldg(a.max_keys + (a.global_max ? 0 : clip));
+            const float g = gkey == 0u ? -10.0f : max_key_decode(gkey);     // (key 0: nothing but silent tiles)
+            const float floor_lg = g - 8.0f;
+            const float floor_y = ((g - 8.0f) + 4.0f) * 0.25f;
+            value = floor_y;
+            if (a.tile_keys != nullptr) {
+                const uint32_t kmax = __ldg(a.tile_keys + 2 * tile), kmin = __ldg(a.tile_keys + 2 * tile + 1);
+                if (kmax == 0u) {                // never stored: all its samples were zero, every value is log10(1e-10) = -10
+                    action = 2;
+                    value = floor_lg > -10.0f ? floor_y : (floor_lg != floor_lg ? floor_y : -1.5f);
+                } else {
+                    const float tile_max = max_key_decode(kmax), tile_min = max_key_decode(~kmin);
+                    if (!(tile_min >= floor_lg)) action = tile_max < floor_lg ? 2 : 1;
+                }
             } else {
-                const float tile_max = max_key_decode(kmax), tile_min = max_key_decode(~kmin);
-                if (!(tile_min >= floor_lg)) action = tile_max < floor_lg ? 2 : 1;
+                const float smallest = max_key_decode(~__ldg(a.min_keys + clip));
+                if (!(smallest >= floor_lg)) action = 1;
             }
-        } else {
-            const float smallest = max_key_decode(~__ldg(a.min_keys + clip));
-            if (!(smallest >= floor_lg)) action = 1;
+            frames = a.n_frames - t0 < kTcTileFrames ? a.n_frames - t0 : kTcTileFrames;
+            tile_out = reinterpret_cast<OutT*>(a.out) + clip * NM * static_cast<int64_t>(a.n_frames) + t0;
         }
-        if (action == 0) continue;
-        const int frames = a.n_frames - t0 < kTcTileFrames ? a.n_frames - t0 : kTcTileFrames;
-        OutT* tile_out = reinterpret_cast<OutT*>(a.out) + clip * NM * static_cast<int64_t>(a.n_frames) + t0;
-        if (action == 2) fill_tile_tc<NM, OutT>(tile_out, a.n_frames, frames, fill_value, lane);
-        else normalise_tile_tc<NM, OutT>(tile_out, a.n_frames, frames, floor_y, lane);
+        const bool any = __syncthreads_or(action != 0);
+        if (!any) continue;                  // (block-uniform)
+        if (lane == 0) work[warp] = Work{tile_out, value, frames, action};
+        __syncthreads();
+#pragma unroll 1
+        for (int w = 0; w < kFinishWarps; ++w) {
+            const Work job = work[w];
+            if (job.action == 2) fill_tile_rows<NM, OutT>(job.out, a.n_frames, job.frames, job.value, warp, lane);
+            else if (job.action == 1) normalise_tile_rows<NM, OutT>(job.out, a.n_frames, job.frames, job.value, warp, lane);
+        }
+        __syncthreads();                     // the list is rewritten in the next round
     }
 }
 
@@ -1178,7 +1199,7 @@ cudaError_t launch_tc_finish(const LogmelArgs& a, cudaStream_t stream) {
     ProfileScope profile(1, stream);
     cudaLaunchConfig_t config = {};
     config.gridDim = dim3(grid);
-    config.blockDim = dim3(256);
+    config.blockDim = dim3(32 * kFinishWarps);
     config.dynamicSmemBytes = 0;
     config.stream = stream;
     cudaLaunchAttribute attr[1];
