@@ -63,7 +63,7 @@ constexpr uint32_t kWaitHintNs = 20000;      // suspend-time hint of one try_wai
 constexpr int kTraceTiles = 8, kTraceEvents = 16, kTraceRoles = 6;
 constexpr int kTraceWords = kTraceRoles * kTraceTiles * kTraceEvents + 8;
 #if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
-// (bring-up switches ride in the upper bits of trace_first: 0x400 = no L2 prefetch, 0x800 = bulk instead of tensor L2 prefetch, 0x1000 = no finish in the epilogue, 0x2000 = no mel sums, 0x4000 = never repeat the E sweep, 0x8000 = one chunk per fold warp and sweep - measurement only, wrong results)
+// (bring-up switches ride in the upper bits of trace_first: 0x400 = no L2 prefetch, 0x800 = bulk instead of tensor L2 prefetch, 0x1000 = no finish in the epilogue, 0x2000 = no mel sums, 0x4000 = never repeat the E sweep, 0x8000 = one chunk per fold warp and sweep, 0x10000 = no short cut for digital silence - measurement only, wrong results)
 #define TC_DEBUG_FLAG(bit) ((trace_first_arg & (bit)) != 0)
 #else
 #define TC_DEBUG_FLAG(bit) false
@@ -339,12 +339,12 @@ struct TileCursor {
         step_t0 = static_cast<int>(grid % tpc) * kTcTileFrames;
         frames_per_clip = tiles_per_clip * kTcTileFrames;
     }
-    __device__ __forceinline__ TileCoord peek_next() const {
-        TileCoord n = at;
+    __device__ __forceinline__ TileCoord next_of(TileCoord n) const {
         n.clip += step_clips; n.t0 += step_t0;
         if (n.t0 >= frames_per_clip) { n.t0 -= frames_per_clip; ++n.clip; }
         return n;
     }
+    __device__ __forceinline__ TileCoord peek_next() const { return next_of(at); }
     __device__ __forceinline__ void advance() { at = peek_next(); }
 };
 
@@ -378,19 +378,20 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gm
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
 }
 
-__device__ __forceinline__ int64_t valid_samples(const LogmelArgs& a, int64_t clip) {
-    int64_t valid = a.n_samples;
-    if (a.lengths != nullptr) {
-        const int64_t len = a.lengths[clip];
-        valid = len < 0 ? 0 : (len < valid ? len : valid);
-    }
-    return valid;
+// The real samples of an utterance: `lengths[clip]` clamped to the row, or the whole row.  The fold warps fetch the raw
+// length a few tiles ahead (length_of) - a load from global memory at the top of a tile would sit on their critical path.
+__device__ __forceinline__ int32_t length_of(const LogmelArgs& a, int64_t clip) {
+    return (a.lengths != nullptr && clip < a.batch) ? __ldg(a.lengths + clip) : 0;
+}
+__device__ __forceinline__ int64_t valid_from(const LogmelArgs& a, int32_t length) {
+    if (a.lengths == nullptr) return a.n_samples;
+    const int64_t len = length;
+    return len < 0 ? 0 : (len < a.n_samples ? len : a.n_samples);
 }
 
 // how half h of the tile at `tc` reaches shared memory (same answer in the loader warp and in the fold warps)
 template <typename InT>
-__device__ __forceinline__ int half_mode(const LogmelArgs& a, int tma_rows, const TileCoord& tc, int h) {
-    const int64_t valid = valid_samples(a, tc.clip);
+__device__ __forceinline__ int half_mode(const LogmelArgs& a, int tma_rows, const TileCoord& tc, int h, int64_t valid) {
     const int64_t s0 = static_cast<int64_t>(tc.t0 + kTcHalfFrames * h) * kHop - kHalfWin;     // first sample of the half
     if constexpr (sizeof(InT) == 4) {
         if (tma_rows <= 0) return kModeCoop;
@@ -519,9 +520,8 @@ __device__ __forceinline__ void expand_pcm_half(float* s_half, int pt, int bar_i
 
 // cooperative mode, the half's fold threads
 template <typename InT>
-__device__ __forceinline__ void produce_half(const LogmelArgs& a, const TileCoord& tc, int h, float* s_half, int pt, int bar_id) {
+__device__ __forceinline__ void produce_half(const LogmelArgs& a, const TileCoord& tc, int h, float* s_half, int pt, int bar_id, int64_t valid) {
     const InT* __restrict__ row = static_cast<const InT*>(a.audio) + tc.clip * a.stride_b;
-    const int64_t valid = valid_samples(a, tc.clip);
     const int64_t s0 = static_cast<int64_t>(tc.t0 + kTcHalfFrames * h) * kHop - kHalfWin;
     const bool aligned = sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");   // all four warps are done reading the previous tile's rows
@@ -631,6 +631,48 @@ __device__ __forceinline__ float sweep_store(int sweep, uint32_t scale, int j0, 
 static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) == 96 && tc_hi_col(3) - tc_hi_col(2) == 96 &&
               tc_left_col(1) - tc_left_col(0) == 6 && tc_left_col(3) - tc_left_col(2) == 6, "column arithmetic of sweep_store");
 
+// ---- digital silence ---------------------------------------------------------------------------------
+// A lane quadrant whose samples are ALL zero (the zero tail pad_or_trim appends, the 30 s of padding transcribe asks for,
+// `lengths`) needs no arithmetic: its operand is zeros.  The test reads the quadrant's 34 rows (lane = row; lanes 0 and 1
+// take rows 32 and 33 as well) - but only after a look at four samples per lane has found nothing but zeros, so a tile
+// of sound pays one load and a vote.  -0.0 counts as zero (its power is 0 as well); NaN / Inf do not.
+__device__ __forceinline__ bool quadrant_is_silent(uint32_t quad_rows, uint32_t fr, int lane) {
+    const float4 q = lds128(fr);
+    const uint32_t first = (__float_as_uint(q.x) | __float_as_uint(q.y) | __float_as_uint(q.z) | __float_as_uint(q.w)) & 0x7fffffffu;
+    if (__any_sync(0xffffffffu, first != 0u)) return false;
+    uint32_t bits = 0u;
+    const uint32_t row = quad_rows + lane * (kTcRowPitch * 4);
+#pragma unroll 4
+    for (int c = 0; c < kHop / 4; ++c) {
+        const float4 v = lds128(row + 16 * c);
+        bits |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
+    }
+    if (lane < 2) {
+        const uint32_t tail = row + 32 * (kTcRowPitch * 4);
+#pragma unroll 4
+        for (int c = 0; c < kHop / 4; ++c) {
+            const float4 v = lds128(tail + 16 * c);
+            bits |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
+        }
+    }
+    return !__any_sync(0xffffffffu, (bits & 0x7fffffffu) != 0u);
+}
+// the chunks [j0, j1) of a sweep's two units as zeros (same columns as sweep_store)
+__device__ __forceinline__ void sweep_store_zeros(int sweep, int j0, int j1, uint32_t lane_addr) {
+    const uint32_t z[4] = {0u, 0u, 0u, 0u};
+    uint32_t c = lane_addr + (sweep == 0 ? tc_hi_col(0) : tc_hi_col(2)) + 4 * j0;
+#pragma unroll 1
+    for (int j = j0; j < j1; ++j, c += 4) {
+        if (j < 2 * kTcMainSteps) {
+            tmem_st4(c, z); tmem_st4(c + 48, z);
+            tmem_st4(c + 96, z); tmem_st4(c + 144, z);
+        } else {
+            const uint32_t b1 = lane_addr + (sweep == 0 ? tc_left_col(0) : tc_left_col(2));
+            tmem_st4(b1, z); tmem_st4(b1 + 4, z); tmem_st4(b1 + 8, z);     // 12 columns: both units' [hi x 3 | lo x 3]
+        }
+    }
+}
+
 // ---- epilogue ---------------------------------------------------------------------------------------
 // ---- finish a tile: log10 clamp, coalesced row stores (lane = frame), extremes; leaves acc zeroed ----
 // `at`: the tile; k: its index among the CTA's tiles; y_offset / silent: what the folds said about it (see epilogue_role)
@@ -739,27 +781,47 @@ __device__ __forceinline__ void epilogue_role(const LogmelArgs& a, long long* tr
             }
             // Re and Im of a bin take the same weights: units 0 / 2 (even bins) share one body, units 1 / 3 (odd bins) the other.
             // The columns come in L::pieces pieces; the accumulator is released once the last piece is in registers.
-#pragma unroll
-            for (int piece = 0; piece < L::pieces; ++piece) {
+            // (a tile of digital silence: the tensor cores were not asked anything - see the issue warp - and the sums stay zero)
+            if constexpr (kDeferFinish) {
                 float d[L::piece_cols];
-                tmem_ld_cols<L::piece_cols>(d_addr + piece * L::piece_cols, d);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (piece == L::pieces - 1) {
+                if (!silent) {
+                    tmem_ld_cols<L::piece_cols>(d_addr, d);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->d_empty);   // the next unit may overwrite the accumulator
+                if (quad == 0) TC_TRACE(4, ti, 3 * u + 1);
+                if (u == 0 && k > 0) epilogue_finish_tile<NM, OutT, PITCH>(a, trace, trace_first_arg, acc, done, k - 1, y_done, silent_done, quad, lane);
+                if (silent || TC_DEBUG_FLAG(0x2000)) continue;   // (0x2000, measurement only: pull and release, no mel sums)
+                if ((u & 1) == 0) tc_epilogue_unit<NM, 0, 0, L::piece_cols>(d, acc);
+                else tc_epilogue_unit<NM, 1, 0, L::piece_cols>(d, acc);
+            } else {
+                if (silent) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->d_empty);   // the next unit may overwrite the accumulator
-                    if (quad == 0) TC_TRACE(4, ti, 3 * u + 1);
+                    if (lane == 0) mbar_arrive(&bars->d_empty);
+                    continue;
                 }
-                if constexpr (kDeferFinish) {
-                    if (u == 0 && k > 0) epilogue_finish_tile<NM, OutT, PITCH>(a, trace, trace_first_arg, acc, done, k - 1, y_done, silent_done, quad, lane);
-                }
-                if (TC_DEBUG_FLAG(0x2000)) continue;   // (measurement only: pull and release, no mel sums)
-                if ((u & 1) == 0) {
-                    if (piece == 0) tc_epilogue_unit<NM, 0, 0, L::piece_cols>(d, acc);
-                    else tc_epilogue_unit<NM, 0, (L::pieces - 1) * L::piece_cols, L::piece_cols>(d, acc);
-                } else {
-                    if (piece == 0) tc_epilogue_unit<NM, 1, 0, L::piece_cols>(d, acc);
-                    else tc_epilogue_unit<NM, 1, (L::pieces - 1) * L::piece_cols, L::piece_cols>(d, acc);
+#pragma unroll
+                for (int piece = 0; piece < L::pieces; ++piece) {
+                    float d[L::piece_cols];
+                    tmem_ld_cols<L::piece_cols>(d_addr + piece * L::piece_cols, d);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (piece == L::pieces - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->d_empty);   // the next unit may overwrite the accumulator
+                        if (quad == 0) TC_TRACE(4, ti, 3 * u + 1);
+                    }
+                    if (TC_DEBUG_FLAG(0x2000)) continue;   // (measurement only: pull and release, no mel sums)
+                    if ((u & 1) == 0) {
+                        if (piece == 0) tc_epilogue_unit<NM, 0, 0, L::piece_cols>(d, acc);
+                        else tc_epilogue_unit<NM, 0, (L::pieces - 1) * L::piece_cols, L::piece_cols>(d, acc);
+                    } else {
+                        if (piece == 0) tc_epilogue_unit<NM, 1, 0, L::piece_cols>(d, acc);
+                        else tc_epilogue_unit<NM, 1, (L::pieces - 1) * L::piece_cols, L::piece_cols>(d, acc);
+                    }
                 }
             }
             if (quad == 0) TC_TRACE(4, ti, 3 * u + 2);
@@ -848,29 +910,35 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         const uint32_t fr = quad_rows + lane * (kTcRowPitch * 4);
         const int half_bar = 9 + half;                                        // named barrier of the half's four warps
         // the copy of half h of the tile at `tp` (one thread): tensor copy, bulk copy of PCM samples, or nothing
-        auto issue_half = [&](const TileCoord& tp) {
-            const int mode = half_mode<InT>(a, tma_rows, tp, half);
+        auto issue_half = [&](const TileCoord& tp, int64_t valid) {
+            const int mode = half_mode<InT>(a, tma_rows, tp, half, valid);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the rows were read through the generic proxy
             if (mode == kModeTma) tma_load_half(&audio_map, tp, half, s_half, &bars.audio_full[half]);
             else if (mode == kModePcm) pcm_load_half(a, tp, half, s_half, &bars.audio_full[half]);
         };
-        auto prefetch_half = [&](const TileCoord& tp) {
+        auto prefetch_half = [&](const TileCoord& tp, int64_t valid) {
             if (TC_DEBUG_FLAG(0x400)) return;
-            if (half_mode<InT>(a, tma_rows, tp, half) == kModeTma && !TC_DEBUG_FLAG(0x800)) tma_prefetch_half(&audio_map, tp, half);
+            if (half_mode<InT>(a, tma_rows, tp, half, valid) == kModeTma && !TC_DEBUG_FLAG(0x800)) tma_prefetch_half(&audio_map, tp, half);
             else prefetch_half_l2<InT>(a, tp, half);
         };
         uint32_t parity = 0, full_parity = 0;
         uint32_t last_scale = 5u;                                             // (2^12: right for samples of order 1)
         int ti = 0;
         TileCursor cursor(tiles_per_clip);
+        // the utterance lengths of this tile, the next one and the one after (the tiles whose copy / L2 prefetch this one issues)
+        int32_t len_cur = length_of(a, cursor.at.clip), len_next = length_of(a, cursor.peek_next().clip),
+                len_after = length_of(a, cursor.next_of(cursor.peek_next()).clip);
         if (part == 0 && (quad & 1) == 0 && lane == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) {   // warps 0 and 2
-            issue_half(cursor.at);
-            if (static_cast<int64_t>(blockIdx.x) + gridDim.x < total_tiles) prefetch_half(cursor.peek_next());
+            issue_half(cursor.at, valid_from(a, len_cur));
+            if (static_cast<int64_t>(blockIdx.x) + gridDim.x < total_tiles) prefetch_half(cursor.peek_next(), valid_from(a, len_next));
         }
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, cursor.advance()) {
             if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 0);
             const TileCoord tcl = cursor.at;
-            const int mode = half_mode<InT>(a, tma_rows, tcl, half);
+            // (in flight while this tile is folded)
+            const int32_t len_far = length_of(a, cursor.next_of(cursor.next_of(cursor.peek_next())).clip);
+            const int64_t valid_cur = valid_from(a, len_cur);
+            const int mode = half_mode<InT>(a, tma_rows, tcl, half, valid_cur);
             if (mode == kModeTma) {
                 if constexpr (sizeof(InT) == 4) {
                     if (half_needs_patch(tma_rows, tcl, half)) {
@@ -890,9 +958,11 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 full_parity ^= 1u;
                 expand_pcm_half(s_half, half_thread, half_bar);
             } else {
-                produce_half<InT>(a, tcl, half, s_half, half_thread, half_bar);
+                produce_half<InT>(a, tcl, half, s_half, half_thread, half_bar, valid_cur);
             }
             if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 1);
+            // (the quadrant's three warps read the same rows: the same answer, no exchange)
+            const bool quad_zero = quadrant_is_silent(quad_rows, fr, lane) && !TC_DEBUG_FLAG(0x10000);
             uint32_t scale = last_scale;
 #pragma unroll 1
             for (int sweep = 0; sweep < 2; ++sweep) {
@@ -903,7 +973,14 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 // that the warps come out at 9 / 8 / 9 chunks per tile
                 const int slot = sweep == 0 ? part : kFoldParts - 1 - part;
                 const int j0 = slot == 0 ? 0 : 1 + 4 * slot, j1 = TC_DEBUG_FLAG(0x8000) ? j0 + 1 : 5 + 4 * slot;   // (0x8000, measurement only: one chunk per warp and sweep)
-                if (sweep == 0) {
+                if (quad_zero) {
+                    // nothing but zeros: the operand is zeros, the scale step stays, the tile info says so
+                    sweep_store_zeros(sweep, j0, j1, lane_addr);
+                    if (sweep == 0 && part == 0 && lane == 0) {
+                        *reinterpret_cast<volatile uint32_t*>(&info.scale[ti & 1][quad]) = scale;
+                        *reinterpret_cast<volatile uint32_t*>(&info.silent[ti & 1][quad]) = 1u;
+                    }
+                } else if (sweep == 0) {
                     // the E sweep with the previous tile's scale step, tracking the largest |sample|; the quadrant's two warps
                     // then agree on the step this tile calls for and repeat their chunks if it is another one
                     const float m = sweep_store<true>(0, scale, j0, j1, fr, lane_addr);
@@ -941,13 +1018,8 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                             *reinterpret_cast<volatile uint32_t*>(&info.released[half]) = 0u;
                             if (tile + gridDim.x < total_tiles) {
                                 const TileCoord next = cursor.peek_next();
-                                issue_half(next);
-                                if (tile + 2 * static_cast<int64_t>(gridDim.x) < total_tiles) {
-                                    TileCoord after = next;
-                                    after.clip += cursor.step_clips; after.t0 += cursor.step_t0;
-                                    if (after.t0 >= cursor.frames_per_clip) { after.t0 -= cursor.frames_per_clip; ++after.clip; }
-                                    prefetch_half(after);
-                                }
+                                issue_half(next, valid_from(a, len_next));
+                                if (tile + 2 * static_cast<int64_t>(gridDim.x) < total_tiles) prefetch_half(cursor.next_of(next), valid_from(a, len_after));
                             }
                         }
                     }
@@ -955,6 +1027,9 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 4 + 3 * sweep);
             }
             parity ^= 1u;
+            len_cur = len_next;
+            len_next = len_after;
+            len_after = len_far;
         }
     } else if (warp < kWarpMma) {
         // ===== epilogue warps =====
@@ -972,15 +1047,27 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
             uint32_t a_parity = 0, d_parity = 1;   // d_empty: the first wait passes (accumulator starts free)
             int ti = 0;
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                bool skip_tile = false;
 #pragma unroll 1
                 for (int u = 0; u < kTcUnits; ++u) {
                     const uint32_t sweep_bar = static_cast<uint32_t>(u & 2) << 2;   // byte offset of the sweep's barrier (0 or 8)
                     if ((u & 1) == 0) mbar_wait_addr(a_full0 + sweep_bar, a_parity, ab);
                     TC_TRACE(3, ti, 3 * u);
+                    if (u == 0) {
+                        // a tile of digital silence that the finish kernel will fill (the folds said so before they released
+                        // the E operand): nothing to multiply - the hand-overs below still happen, the commits arrive at once
+                        const volatile uint32_t* z = info.silent[ti & 1];
+                        skip_tile = a.tile_keys != nullptr && (z[0] & z[1] & z[2] & z[3]) != 0u;
+                    }
                     mbar_wait(&bars.d_empty, d_parity, ab);
                     d_parity ^= 1u;
                     TC_TRACE(3, ti, 3 * u + 1);
                     tc_fence_after();
+                    if (skip_tile) {
+                        mma_commit(&bars.d_full);
+                        if (u & 1) mma_commit_addr(a_empty0 + sweep_bar);
+                        continue;
+                    }
                     const TcUnitIssue ui = c_unit_issue[u];
                     // Issue order: the two small products (lo Bh, hi Bl: 2^-11 of the result) first, the main product hi Bh
                     // last.  The tensor cores truncate the fp32 accumulator at every MMA; added in this order only the 7 main
