@@ -281,7 +281,7 @@ def log_mel_spectrogram_batch(
 
     ``audio`` is float32 (any finite range) or int16 PCM (scaled by 1/32768 in-kernel, the
     arithmetic of audio.py:62).  ``lengths`` (optional, ``[B]``) gives the real samples of
-    each row; the rest of the row counts as zeros without being read, i.e. the rows
+    each row; the rest of the row counts as zeros whatever it holds, i.e. the rows
     behave as ``pad_or_trim``-med clips (audio.py:83-86).  ``out_dtype=torch.float16`` stores the float32 result
     rounded to half (what the fp16 model gets after transcribe.py:286's ``.to(dtype)``), halving the bytes written.
     """

@@ -241,7 +241,7 @@ struct TcBarriers {
 
 // what the folds tell the epilogue about a tile: the scale step of each lane quadrant and whether all its samples are
 // zero, [tile parity][quadrant]
-struct TcTileInfo { uint32_t scale[2][4]; uint32_t silent[2][4]; uint32_t quad_max[4][4]; uint32_t released[2]; };
+struct TcTileInfo { uint32_t scale[2][4]; uint32_t silent[2][4]; uint32_t quad_max[4][4]; uint32_t probe[4][4]; uint32_t released[2]; };
 
 // ---- normaliser -------------------------------------------------------------------------------------
 // clamp of an already rescaled value y = (lg + 4) / 4 at floor_y = ((g - 8) + 4) / 4 (NaN when the max is NaN, as in
@@ -396,9 +396,12 @@ __device__ __forceinline__ int half_mode(const LogmelArgs& a, int tma_rows, cons
     if constexpr (sizeof(InT) == 4) {
         if (tma_rows <= 0) return kModeCoop;
         if (valid == a.n_samples) return kModeTma;
+        // `lengths`: a half of real samples, or one the utterance ends in (copied whole, the rows behind the end are zeroed in
+        // shared memory: zero_cut_rows), comes by tensor copy like any other; the zero tail and the rare cut inside the last
+        // rows of the memory row are the warps' business (produce_half)
         const int first = tc.t0 - kTmaLeadRows + kTcHalfFrames * h;
-        if (first < 0 || first + kTcHalfRows > tma_rows) return kModeCoop;
-        return s0 + kHalfSamples <= valid ? kModeTma : kModeCoop;
+        if (first + kTcHalfRows > tma_rows || s0 >= valid) return kModeCoop;
+        return kModeTma;
     } else {
         const uintptr_t src = reinterpret_cast<uintptr_t>(static_cast<const InT*>(a.audio) + tc.clip * a.stride_b) + 2u * static_cast<uint64_t>(s0 < 0 ? 0 : s0);
         return (s0 >= 0 && s0 + kHalfSamples <= valid && (src & 15u) == 0) ? kModePcm : kModeCoop;
@@ -424,7 +427,7 @@ __device__ __forceinline__ bool half_needs_patch(int tma_rows, const TileCoord& 
 // tensor row past the end up to the end of the reflected tail (at most three).
 constexpr int kPatchCand = kTmaLeadRows + 4;
 struct PatchRows { float v[kPatchCand]; int row[kPatchCand]; };
-__device__ __forceinline__ void patch_fetch(const LogmelArgs& a, int tma_rows, const TileCoord& tc, int h, int pt, PatchRows& p) {
+__device__ __forceinline__ void patch_fetch(const LogmelArgs& a, int tma_rows, const TileCoord& tc, int h, int pt, PatchRows& p, int64_t valid) {
     const float* __restrict__ src = static_cast<const float*>(a.audio) + tc.clip * a.stride_b;
     const int c2_first = tc.t0 - kTmaLeadRows;
     const int r_past = tma_rows - c2_first < 0 ? 0 : tma_rows - c2_first;
@@ -438,7 +441,7 @@ __device__ __forceinline__ void patch_fetch(const LogmelArgs& a, int tma_rows, c
         if (p.row[i] >= 0 && pt < kHop) {
             const int64_t pos = static_cast<int64_t>(tc.t0 + r) * kHop - kHalfWin + pt;
             const int64_t idx = reflect_source_index(pos, a.total);
-            if (pos < a.total + kHalfWin && idx >= 0 && idx < a.n_samples) p.v[i] = __ldg(src + idx);
+            if (pos < a.total + kHalfWin && idx >= 0 && idx < valid) p.v[i] = __ldg(src + idx);
         }
     }
 }
@@ -446,6 +449,16 @@ __device__ __forceinline__ void patch_store(const PatchRows& p, float* s_half, i
 #pragma unroll
     for (int i = 0; i < kPatchCand; ++i)
         if (p.row[i] >= 0 && pt < kHop) s_half[p.row[i] * kTcRowPitch + pt] = p.v[i];
+}
+
+// `lengths`: the utterance ends inside this half (copied whole by the TMA unit).  The half's fold threads zero what lies
+// behind its last real sample: thread pt takes column pt of every row.
+__device__ __forceinline__ void zero_cut_rows(float* s_half, int64_t s0, int64_t valid, int pt) {
+    if (pt >= kHop) return;
+    int64_t pos = s0 + pt;
+#pragma unroll 1
+    for (int r = 0; r < kTcHalfRows; ++r, pos += kHop)
+        if (pos >= valid) s_half[r * kTcRowPitch + pt] = 0.f;
 }
 
 __device__ __forceinline__ void tma_load_half(const CUtensorMap* map, const TileCoord& tc, int h, float* s_half, uint64_t* full) {
@@ -520,18 +533,15 @@ __device__ __forceinline__ void expand_pcm_half(float* s_half, int pt, int bar_i
 
 // cooperative mode, the half's fold threads
 template <typename InT>
-__device__ __forceinline__ void produce_half(const LogmelArgs& a, const TileCoord& tc, int h, float* s_half, int pt, int bar_id, int64_t valid) {
+// returns true if nothing was staged because the whole half is zeros (the caller then skips the arithmetic as well)
+__device__ __forceinline__ bool produce_half(const LogmelArgs& a, const TileCoord& tc, int h, float* s_half, int pt, int bar_id, int64_t valid) {
     const InT* __restrict__ row = static_cast<const InT*>(a.audio) + tc.clip * a.stride_b;
     const int64_t s0 = static_cast<int64_t>(tc.t0 + kTcHalfFrames * h) * kHop - kHalfWin;
     const bool aligned = sizeof(InT) == 4 && (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
+    // the whole half lies in the zero tail (`lengths`, right padding) and no reflection reaches a real sample: nothing to stage,
+    // nothing to read (the same answer in all of the half's threads)
+    if (s0 >= valid && valid + kHalfWin < a.total) return true;
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");   // all four warps are done reading the previous tile's rows
-    if (s0 >= valid && valid + kHalfWin < a.total) {
-        // the whole half lies in the zero tail (`lengths`, right padding) and no reflection reaches a real sample
-        float4* z = reinterpret_cast<float4*>(s_half);
-        for (int i = pt; i < kTcHalfWords / 4; i += kHalfThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");
-        return;
-    }
     // chunk c = 40 r + k covers samples s0 + 4c .. + 3 and lands at word 164 r + 4 k
     int r = pt / kChunksPerRow, k = pt - r * kChunksPerRow;
     for (int c = pt; c < kHalfChunks; c += kHalfThreads) {
@@ -555,6 +565,7 @@ __device__ __forceinline__ void produce_half(const LogmelArgs& a, const TileCoor
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kHalfThreads) : "memory");   // every row is written before anybody folds
+    return false;
 }
 
 // ---- fold warps ----------------------------------------------------------------------------------------
@@ -633,29 +644,34 @@ static_assert(tc_lo_col(0) - tc_hi_col(0) == 48 && tc_hi_col(1) - tc_hi_col(0) =
 
 // ---- digital silence ---------------------------------------------------------------------------------
 // A lane quadrant whose samples are ALL zero (the zero tail pad_or_trim appends, the 30 s of padding transcribe asks for,
-// `lengths`) needs no arithmetic: its operand is zeros.  The test reads the quadrant's 34 rows (lane = row; lanes 0 and 1
-// take rows 32 and 33 as well) - but only after a look at four samples per lane has found nothing but zeros, so a tile
-// of sound pays one load and a vote.  -0.0 counts as zero (its power is 0 as well); NaN / Inf do not.
-__device__ __forceinline__ bool quadrant_is_silent(uint32_t quad_rows, uint32_t fr, int lane) {
+// `lengths`) needs no arithmetic: its operand is zeros.  The test reads the quadrant's 34 rows once, shared between its
+// three warps (lane = row, a warp takes every third 16-byte chunk of it; rows 32 and 33 chunk by chunk) - but only after a
+// look at four samples per lane has found nothing but zeros, so a tile of sound pays one load and a vote.  -0.0 counts as
+// zero (its power is 0 as well); NaN / Inf do not.  `probe`: the quadrant's three exchange words.
+__device__ __forceinline__ bool quadrant_is_silent(uint32_t quad_rows, uint32_t fr, int part, int lane, int quad, volatile uint32_t* probe) {
     const float4 q = lds128(fr);
     const uint32_t first = (__float_as_uint(q.x) | __float_as_uint(q.y) | __float_as_uint(q.z) | __float_as_uint(q.w)) & 0x7fffffffu;
-    if (__any_sync(0xffffffffu, first != 0u)) return false;
+    if (__any_sync(0xffffffffu, first != 0u)) return false;      // (the three warps see the same samples: the same branch)
     uint32_t bits = 0u;
     const uint32_t row = quad_rows + lane * (kTcRowPitch * 4);
-#pragma unroll 4
-    for (int c = 0; c < kHop / 4; ++c) {
+#pragma unroll 2
+    for (int c = part; c < kHop / 4; c += kFoldParts) {
         const float4 v = lds128(row + 16 * c);
         bits |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
     }
-    if (lane < 2) {
-        const uint32_t tail = row + 32 * (kTcRowPitch * 4);
-#pragma unroll 4
-        for (int c = 0; c < kHop / 4; ++c) {
-            const float4 v = lds128(tail + 16 * c);
+    {   // rows 32 and 33: 80 chunks over the quadrant's 96 threads
+        const int c = part * 32 + lane;
+        if (c < 2 * (kHop / 4)) {
+            const float4 v = lds128(quad_rows + (32 + c / (kHop / 4)) * (kTcRowPitch * 4) + 16 * (c % (kHop / 4)));
             bits |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
         }
     }
-    return !__any_sync(0xffffffffu, (bits & 0x7fffffffu) != 0u);
+    const bool sound = __any_sync(0xffffffffu, (bits & 0x7fffffffu) != 0u);
+    if (lane == 0) probe[part] = sound ? 1u : 0u;
+    asm volatile("bar.sync %0, %1;" ::"r"(5 + quad), "n"(32 * kFoldParts) : "memory");
+    const uint32_t any_sound = probe[0] | probe[1] | probe[2];
+    asm volatile("bar.sync %0, %1;" ::"r"(5 + quad), "n"(32 * kFoldParts) : "memory");   // (read before the next tile's probe is written)
+    return any_sound == 0u;
 }
 // the chunks [j0, j1) of a sweep's two units as zeros (same columns as sweep_store)
 __device__ __forceinline__ void sweep_store_zeros(int sweep, int j0, int j1, uint32_t lane_addr) {
@@ -939,17 +955,25 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
             const int32_t len_far = length_of(a, cursor.next_of(cursor.next_of(cursor.peek_next())).clip);
             const int64_t valid_cur = valid_from(a, len_cur);
             const int mode = half_mode<InT>(a, tma_rows, tcl, half, valid_cur);
+            bool known_zero = false;
             if (mode == kModeTma) {
                 if constexpr (sizeof(InT) == 4) {
+                    const int64_t s0 = static_cast<int64_t>(tcl.t0 + kTcHalfFrames * half) * kHop - kHalfWin;
+                    const bool cut = s0 + kHalfSamples > valid_cur && valid_cur < a.n_samples;   // (`lengths`: the utterance ends in this half)
                     if (half_needs_patch(tma_rows, tcl, half)) {
                         // a clip's first or last rows: fetch what the zero-filled rows should hold while the copy is in flight
                         PatchRows rows;
-                        patch_fetch(a, tma_rows, tcl, half, half_thread, rows);
+                        patch_fetch(a, tma_rows, tcl, half, half_thread, rows, valid_cur);
                         mbar_wait(&bars.audio_full[half], full_parity, ab);
+                        if (cut) zero_cut_rows(s_half, s0, valid_cur, half_thread);
                         patch_store(rows, s_half, half_thread);
                         asm volatile("bar.sync %0, %1;" ::"r"(half_bar), "n"(kHalfThreads) : "memory");
                     } else {
                         mbar_wait(&bars.audio_full[half], full_parity, ab);
+                        if (cut) {
+                            zero_cut_rows(s_half, s0, valid_cur, half_thread);
+                            asm volatile("bar.sync %0, %1;" ::"r"(half_bar), "n"(kHalfThreads) : "memory");
+                        }
                     }
                     full_parity ^= 1u;
                 }
@@ -958,11 +982,11 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 full_parity ^= 1u;
                 expand_pcm_half(s_half, half_thread, half_bar);
             } else {
-                produce_half<InT>(a, tcl, half, s_half, half_thread, half_bar, valid_cur);
+                known_zero = produce_half<InT>(a, tcl, half, s_half, half_thread, half_bar, valid_cur);
             }
             if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 1);
             // (the quadrant's three warps read the same rows: the same answer, no exchange)
-            const bool quad_zero = quadrant_is_silent(quad_rows, fr, lane) && !TC_DEBUG_FLAG(0x10000);
+            const bool quad_zero = (known_zero || quadrant_is_silent(quad_rows, fr, part, lane, quad, info.probe[quad])) && !TC_DEBUG_FLAG(0x10000);
             uint32_t scale = last_scale;
 #pragma unroll 1
             for (int sweep = 0; sweep < 2; ++sweep) {

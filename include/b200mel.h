@@ -105,7 +105,8 @@ size_t b200mel_workspace_bytes_tiles(int64_t batch, int64_t n_frames);
 /* Replaces log_mel_spectrogram's compute, audio.py:145-156, for a batch of utterances.
  *   audio      device, [batch, n_samples] of `dtype`, row pitch `stride_b` ELEMENTS
  *   lengths    device int32 [batch] or NULL: samples of each row that are real; the rest of the
- *              row is treated as zeros WITHOUT being read (pad_or_trim semantics, audio.py:83-86)
+ *              row counts as zeros whatever it holds (pad_or_trim semantics, audio.py:83-86) and is not
+ *              read beyond the 128-frame tile the utterance ends in (the memory of the row must exist)
  *   right_zero_pad  the `padding` argument (audio.py:145-146); <= 0 is ignored
  *   out        device float32 [batch, n_mels, T] contiguous, T from b200mel_frames (IEEE half with
  *              B200MEL_FLAG_OUT_F16; the pointer is passed through the same parameter)

@@ -115,6 +115,8 @@ def test_lengths_fast_path_equals_zero_filled_rows(b200):
     padded = rows.copy()
     for i, n in enumerate(lens):
         padded[i, min(n, 48000):] = 0.0
+        if i % 2:
+            rows[i, min(n, 48000):] = np.nan      # what lies behind an utterance's end must not matter, whatever it is
     a = b200.log_mel_spectrogram_batch(torch.from_numpy(rows).to(DEV), lengths=torch.from_numpy(lens))
     b = b200.log_mel_spectrogram_batch(torch.from_numpy(padded).to(DEV))
     assert torch.equal(a, b)  # same arithmetic on the same values
