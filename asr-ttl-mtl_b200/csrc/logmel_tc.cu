@@ -241,7 +241,7 @@ struct TcBarriers {
 
 // what the folds tell the epilogue about a tile: the scale step of each lane quadrant and whether all its samples are
 // zero, [tile parity][quadrant]
-struct TcTileInfo { uint32_t scale[2][4]; uint32_t silent[2][4]; uint32_t quad_max[4][4]; uint32_t probe[4][4]; uint32_t released[2]; };
+struct TcTileInfo { uint32_t scale[2][4]; uint32_t silent[2][4]; uint32_t quad_max[4][4]; uint32_t probe[4][4]; uint32_t released[2][2]; };
 
 // ---- normaliser -------------------------------------------------------------------------------------
 // clamp of an already rescaled value y = (lg + 4) / 4 at floor_y = ((g - 8) + 4) / 4 (NaN when the max is NaN, as in
@@ -881,7 +881,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
     }
     if (tid == 32) {
         mbar_init(&bars.audio_full[0], 1); mbar_init(&bars.audio_full[1], 1);
-        info.released[0] = info.released[1] = 0;
+        info.released[0][0] = info.released[0][1] = info.released[1][0] = info.released[1][1] = 0;
         mbar_init(&bars.a_full[0], 4 * kFoldParts); mbar_init(&bars.a_full[1], 4 * kFoldParts);
         mbar_init(&bars.a_empty[0], 1); mbar_init(&bars.a_empty[1], 1);
         mbar_init(&bars.d_full, 1);
@@ -987,6 +987,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
             if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 1);
             // (the quadrant's three warps read the same rows: the same answer, no exchange)
             const bool quad_zero = (known_zero || quadrant_is_silent(quad_rows, fr, part, lane, quad, info.probe[quad])) && !TC_DEBUG_FLAG(0x10000);
+            const int release_sweep = quad_zero ? 0 : 1;   // the pass after which this warp no longer reads the half's rows
             uint32_t scale = last_scale;
 #pragma unroll 1
             for (int sweep = 0; sweep < 2; ++sweep) {
@@ -1034,12 +1035,14 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&bars.a_full[sweep]);
-                    if (sweep == 1) {
-                        // this warp has read the half's rows for the last time; the last of the four warps to say so brings the
-                        // next tile's rows (and asks L2 for the ones after)
+                    if (sweep == release_sweep) {
+                        // this warp has read the half's rows for the last time (at once, if there is nothing but zeros in them);
+                        // the last of the half's warps to say so brings the next tile's rows (and asks L2 for the ones after)
+                        // (one count per tile parity: a warp whose rows are zeros for two tiles in a row may say so for the next
+                        // tile while another one still reads this tile's rows)
                         __threadfence_block();
-                        if (atomicAdd(&info.released[half], 1u) == 2u * kFoldParts - 1u) {
-                            *reinterpret_cast<volatile uint32_t*>(&info.released[half]) = 0u;
+                        if (atomicAdd(&info.released[half][ti & 1], 1u) == 2u * kFoldParts - 1u) {
+                            *reinterpret_cast<volatile uint32_t*>(&info.released[half][ti & 1]) = 0u;
                             if (tile + gridDim.x < total_tiles) {
                                 const TileCoord next = cursor.peek_next();
                                 issue_half(next, valid_from(a, len_next));

@@ -125,6 +125,35 @@ def test_lengths_fast_path_equals_zero_filled_rows(b200):
     assert torch.all(a[0] == -1.5)  # an all-zero utterance (reference: every value (-10+4)/4)
 
 
+def test_lengths_path_with_many_tiles_per_sm(b200):
+    """Every SM walks a dozen tiles, about half of them wholly behind an utterance's end (not staged, not folded, not
+    multiplied) and one per utterance cut by it: the hand-overs between the kernel's warp roles must come out the same as
+    for zero-filled rows, call after call, and no wait may ever time out."""
+    from asr_ttl_mtl_b200 import _native
+
+    rng = np.random.default_rng(77)
+    lens = rng.integers(0, 480001, size=96).astype(np.int64)
+    lens[:4] = [0, 480000, 200, 479999]
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    x = 0.1 * torch.randn(96, 480000, generator=gen, device=DEV)
+    padded = x.clone()
+    padded.masked_fill_(torch.arange(480000, device=DEV)[None, :] >= torch.from_numpy(lens).to(DEV)[:, None], 0.0)
+    want = b200.log_mel_spectrogram_batch(padded)
+    lens_dev = torch.from_numpy(lens).to(DEV).to(torch.int32)
+    b200.log_mel_spectrogram_batch(x, lengths=lens_dev)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    got = [b200.log_mel_spectrogram_batch(x, lengths=lens_dev) for _ in range(8)]
+    stop.record()
+    torch.cuda.synchronize()
+    for g in got:
+        assert torch.equal(g, want)
+    assert _native.kernel_fault() == (0, 0)
+    assert start.elapsed_time(stop) / 8 < 20.0, "a front-end call over 96 clips takes well under a millisecond; a timed-out wait tens"
+    for i in (0, 1, 2, 3, 50):
+        assert _maxerr(want[i], orc.logmel_f32_port(padded[i].cpu().numpy(), 80)) <= TOL
+
+
 def test_variable_length_clips_like_the_training_set(b200):
     # BASELINE config 4: 1-30 s clips pad_or_trim-med to N_SAMPLES, batches of 16
     lens = signals.variable_lengths(16)
