@@ -546,6 +546,33 @@ def run_own_arm(args) -> None:
                         "padded_audio_hours_per_s": B * n_v * CLIP_SECONDS / 3600.0 / (ms_v / 1e3)}
         configs["config4"] = c4
         del var, out_v
+
+        # config 1, this arm: ONE 30 s clip through the drop-in call the unchanged dataset path makes (dataset.py:82-89):
+        # NumPy in, CPU tensor out - H2D, kernel and D2H of a single utterance, wall clock per call
+        g0 = torch.Generator().manual_seed(0)
+        one = (0.1 * torch.randn(N_SAMPLES, generator=g0)).numpy()
+        for _ in range(3):
+            b200.log_mel_spectrogram(one, n_mels)
+        laps = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            b200.log_mel_spectrogram(one, n_mels)
+            laps.append(time.perf_counter() - t0)
+        one_dev = torch.from_numpy(one).to(device)
+        for _ in range(3):
+            b200.log_mel_spectrogram(one_dev, n_mels)
+        torch.cuda.synchronize()
+        dev_laps = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            b200.log_mel_spectrogram(one_dev, n_mels)
+            torch.cuda.synchronize()
+            dev_laps.append(time.perf_counter() - t0)
+        configs["config1"] = {
+            "workload": "one synthetic 30 s clip through log_mel_spectrogram (BASELINE config 1, this arm)",
+            "host_in_host_out_ms_median_of_30": 1e3 * statistics.median(laps),
+            "device_in_device_out_ms_median_of_30": 1e3 * statistics.median(dev_laps),
+            "value": CLIP_SECONDS / 3600.0 / statistics.median(laps), "unit": "audio-hours/s"}
         extra["configs"] = configs
 
         # ---- sustained: >= 2 s of back-to-back steps, clocks sampled while they run (last: it leaves the GPU at its power cap) ----

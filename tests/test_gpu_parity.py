@@ -517,3 +517,27 @@ def test_normalise_entry_point(b200, native_lib):
     torch.cuda.synchronize()
     want = (torch.maximum(vals, vals.amax(dim=1, keepdim=True) - 8.0) + 4.0) / 4.0
     assert torch.equal(out, want)
+
+
+def test_abi_without_tile_keys_equals_the_wrapper(b200, native_lib, default_variant):
+    """The binding of INTEGRATION.md section 2 sizes the workspace with b200mel_workspace_bytes and passes no
+    B200MEL_FLAG_TILE_KEYS: zero-padded clips (digital silence is then computed and stored like any other tile, the clamp
+    decided per utterance) must come out as through the Python mirror, which passes per-tile keys."""
+    from asr_ttl_mtl_b200 import _native, audio
+
+    n = 16000 * 9
+    clips = np.zeros((6, n), dtype=np.float32)
+    for i in range(6):
+        k = [n, n // 2, 3000, 0, n - 1, 20000][i]
+        clips[i, :k] = signals.make_signal("gauss", k, 700 + i) if k > 0 else 0
+    x = torch.from_numpy(clips).to(DEV)
+    want = b200.log_mel_spectrogram_batch(x)
+    frames = _native.frames(n, 0)
+    out = torch.empty(6, 80, frames, device=DEV)
+    ws = torch.empty(native_lib.b200mel_workspace_bytes(6), dtype=torch.uint8, device=DEV)
+    variant = {"fft": _native.VARIANT_FFT, "tcgen05": _native.VARIANT_TCGEN05}[default_variant]
+    _native.check(native_lib.b200mel_logmel_device(audio._plan(0, 80), x.data_ptr(), _native.DTYPE_F32, 6, n, n, None, 0, out.data_ptr(),
+                                                   ws.data_ptr(), 0, variant, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    assert torch.all(out[3] == -1.5)
