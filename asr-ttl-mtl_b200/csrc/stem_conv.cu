@@ -430,17 +430,20 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
 cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, const uint32_t* tile_keys, int global_max, int64_t batch, int n_frames, const float* weight,
                                    const float* bias, int n_state, float* out, cudaStream_t stream) {
     if (batch <= 0 || n_frames <= 0) return cudaSuccess;
-    static bool configured = false;
-    cudaError_t err;
-    if (!configured) {
-        err = cudaFuncSetAttribute(stem_conv1_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
-        if (err != cudaSuccess) return err;
-        configured = true;
-    }
-    int device = 0, sms = 0;
-    err = cudaGetDevice(&device);
-    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    constexpr int kMaxDevices = 64;
+    static int sms_by_device[kMaxDevices] = {0};                      // (also: the kernel's attributes are set on this device)
+    int device = 0;
+    cudaError_t err = cudaGetDevice(&device);
     if (err != cudaSuccess) return err;
+    if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (sms_by_device[device] == 0) {
+        err = cudaFuncSetAttribute(stem_conv1_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
+        int count = 0;
+        if (err == cudaSuccess) err = cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device);
+        if (err != cudaSuccess) return err;
+        sms_by_device[device] = count;
+    }
+    const int sms = sms_by_device[device];
     const int slices = n_state / kStemN;
     const int64_t tiles = batch * ((n_frames + kStemTile - 1) / kStemTile);
     int64_t walkers = sms / slices;                                   // CTAs per slice; every CTA of the grid is resident
