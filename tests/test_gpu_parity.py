@@ -541,3 +541,24 @@ def test_abi_without_tile_keys_equals_the_wrapper(b200, native_lib, default_vari
     torch.cuda.synchronize()
     assert torch.equal(out, want)
     assert torch.all(out[3] == -1.5)
+
+
+def test_front_end_call_can_be_captured_in_a_cuda_graph(b200):
+    """The library only enqueues work on the caller's stream (one memset, the front-end kernel, the finish kernel): the
+    whole call can be captured once and replayed on new data - what a training loop with a fixed batch shape does."""
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    x1 = 0.1 * torch.randn(16, 480000, generator=gen, device=DEV)
+    x2 = 0.1 * torch.randn(16, 480000, generator=gen, device=DEV)
+    x2[3, 100000:] = 0.0
+    static_in = x1.clone()
+    out = torch.empty(16, 80, 3000, device=DEV)
+    b200.log_mel_spectrogram_batch(static_in, out=out)          # plans, module loading: outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        b200.log_mel_spectrogram_batch(static_in, out=out)
+    for x in (x1, x2, x1):
+        static_in.copy_(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, b200.log_mel_spectrogram_batch(x))
