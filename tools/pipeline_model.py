@@ -46,6 +46,56 @@ def simulate(n=60, tL=1900, tFE=4300, tFO=4300, tM=1100, tX=350, tC=550, tF=2700
     period = (tile_done[n - 1] - tile_done[n - 21]) / 20
     return period
 
+
+# ---- round 2: the kernel as it ships (fold warps issue the tile copy themselves after the O sweep, single accumulator,
+# finish after the tile's last unit) against a 3-slot operand ring with two accumulators.  Durations from
+# profiles/r02_tc80_cta0_timeline.txt.  `cur` reproduces the measured ~10 k cycles per tile; the ring gains ~3 %.
+def simulate_r2(mode, n=80, tL=1700, tE=3640, tO=2840, tM=1100, tX=500, tC=700, tF=3300, h=100, finish_split=False, tEscale=1.0):
+    tE*=tEscale; tO*=tEscale
+    mma_done={}; pull_done={}; a_full={}
+    audio_full={0:tL}
+    mma_free=0; epi_free=0
+    E_end={}; O_end={}
+    tile_done={}
+    # event-driven by iterating tiles in order; dependencies only go backward except O(i) on mma_done(4i) in ring mode.
+    for i in range(n):
+        # E sweep
+        if mode=='cur':
+            dep = mma_done.get(4*(i-1)+1,0)
+        else:
+            dep = mma_done.get(4*(i-1)+2,0)
+        sE=max(audio_full[i], dep+h, O_end.get(i-1,0))
+        E_end[i]=sE+tE
+        a_full[4*i]=a_full[4*i+1]=E_end[i]+h
+        # MMA u0,u1 (need to interleave with epilogue) -> process units sequentially with epilogue
+        def do_unit(g):
+            nonlocal mma_free, epi_free
+            if mode=='cur': dfree = pull_done.get(g-1,0)
+            else: dfree = pull_done.get(g-2,0)
+            st=max(mma_free, a_full[g], dfree+h)
+            mma_done[g]=st+tM
+            mma_free=st+tM*0.9
+            xs=max(epi_free, mma_done[g]+h)
+            pull_done[g]=xs+tX
+            epi_free=pull_done[g]+tC
+            if g%4==3:
+                epi_free+=tF
+                tile_done[g//4]=epi_free
+        do_unit(4*i)
+        if mode=='cur':
+            depO = mma_done.get(4*(i-1)+3,0)
+        else:
+            depO = max(mma_done.get(4*(i-1)+3,0), mma_done[4*i])
+        # u1 doesn't depend on O
+        do_unit(4*i+1)
+        sO=max(E_end[i], depO+h)
+        O_end[i]=sO+tO
+        a_full[4*i+2]=a_full[4*i+3]=O_end[i]+h
+        audio_full[i+1]=O_end[i]+h+tL
+        do_unit(4*i+2); do_unit(4*i+3)
+    return (tile_done[n-1]-tile_done[n-21])/20
+
+
 if __name__ == "__main__":
     base = dict()
     for name, kw in [
@@ -63,3 +113,6 @@ if __name__ == "__main__":
         ("8-warp sweeps, finish 0 (ideal second accumulator-ish)", dict(fold="all8", tF=0)),
     ]:
         print(f"{simulate(**kw):8.0f} cycles/tile  {name}")
+    print("-- round 2 model")
+    for kw in [dict(), dict(tF=0), dict(tL=0), dict(tF=0, tL=0), dict(tF=1650), dict(tF=2300), dict(tC=350, tF=1650)]:
+        print(f"{simulate_r2('cur', **kw):8.0f} cycles/tile as shipped   {simulate_r2('ring', **kw):8.0f} with the operand ring   {kw}")
