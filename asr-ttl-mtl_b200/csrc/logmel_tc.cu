@@ -25,8 +25,13 @@
 //     warps           run the same code, which is what the instruction cache wants) pulls the 104 accumulator columns
 //                     into registers (tcgen05.ld), releases the accumulator, and adds w d^2 to the mels
 //                     of each bin - mel structure and weights are compile-time constants (FFMA immediates),
-//                     partial sums in registers; after the 4th unit: 2^-2k, log10(max(., 1e-10)), (x + 4) / 4, 128-byte
-//                     coalesced row stores, the utterance's and the tile's extremes (warp REDUX + atomicMax).
+//                     partial sums in registers.  A tile is finished - log2 on the MUFU, ONE fused multiply-add for
+//                     (log10 + 4) / 4 with the data scale 2^-2k in its addend, the 1e-10 clamp as max(., -1.5), 128-byte
+//                     coalesced row stores (immediate offsets when the output pitch is the usual 3000 frames), the
+//                     utterance's and the tile's extremes (warp REDUX + atomicMax) - after the NEXT tile's first unit has
+//                     been pulled (80 mels), so the tensor cores never wait for the stores.
+// Digital silence (zero padding, `lengths`) is cheap: a lane quadrant whose rows are all zeros gets a zero operand instead
+// of the sweeps and hands its rows back at once; a tile of nothing but silence is neither multiplied nor pulled nor stored.
 // No CTA ever waits for another one - there is no cross-CTA hand-over at all - so the kernel makes progress with any
 // number of co-resident CTAs.  What is left of the normalisation, the clamp at max - 8, needs every tile of an utterance:
 // the FINISH kernel right behind (tc_finish_kernel, a warp per tile) decides from the utterance's and the tile's extremes
