@@ -89,6 +89,19 @@ def main():
                   f"{(got['tcgen05'][c] == e1).mean() * 100:.2f} %   |emul(exact) - f64| {np.abs(e0 - f64[c]).max():.3e}  "
                   f"|emul(RZ) - f64| {np.abs(e1 - f64[c]).max():.3e}  |ref - f64| {e_ref[c].max():.3e}")
 
+    print("== every signal family at full length: 8 clips of 30 s each (80 clips), both mel counts, every value")
+    kinds = list(signals.KINDS)
+    clips = np.stack([signals.make_signal(k, 480000, 7000 + 10 * i + j) for i, k in enumerate(kinds) for j in range(8)])
+    xk = torch.from_numpy(clips).cuda()
+    for n_mels in (80, 128):
+        ref = orc.logmel_f32_port_per_utterance(torch.from_numpy(clips), n_mels).numpy()
+        f64 = np.stack([orc.logmel_f64(c, n_mels) for c in clips])
+        for v in ("tcgen05", "fft"):
+            y = b.log_mel_spectrogram_batch(xk, n_mels=n_mels, variant=v).cpu().numpy()
+            per_kind = [f"{k} {np.abs(y[8 * i:8 * i + 8] - ref[8 * i:8 * i + 8]).max():.1e}" for i, k in enumerate(kinds)]
+            print(f"   n_mels={n_mels} {v:8s} |gpu - ref| max {np.abs(y - ref).max():.3e}  |gpu - f64| max {np.abs(y - f64).max():.3e}  "
+                  f"|ref - f64| max {np.abs(ref - f64).max():.3e}   per family: " + ", ".join(per_kind))
+
     print("== amplitude ladder: 4 clips of 5 s of randn x scale, 80 mel")
     for scale in (1e-6, 1e-4, 1e-2, 1.0, 100.0, 3276.8, 32768.0, 1e6):
         clips = np.stack([(scale * np.random.default_rng(50 + i).standard_normal(80000)).astype(np.float32) for i in range(4)])
