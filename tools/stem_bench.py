@@ -55,6 +55,12 @@ def main():
     print(f"torch conv1d+gelu fp32    {t_torch_fp32:8.4f} ms")
     print(f"torch conv1d+gelu fp16 (incl. casts) {half:8.4f} ms")
     err = (out[:4].double() - F.gelu(F.conv1d(mel[:4].double(), w.double(), bias.double(), padding=1))).abs().max().item()
+    # what the memory system gives a stream with the stem's read : write mix (1 : 4.8): a plain fill of the output and a
+    # copy of a mel-sized block next to it, on the same buffers
+    t_fill = timed(lambda: out.fill_(1.0), reps)
+    t_mix = timed(lambda: (out.fill_(1.0), mel.clone()), reps)
+    print(f"fill of the stem's output {t_fill:8.4f} ms  {out.numel() * 4 / t_fill / 1e6:8.1f} GB/s written")
+    print(f"fill + clone of the mel   {t_mix:8.4f} ms  {(out.numel() * 4 + 2 * mel.numel() * 4) / t_mix / 1e6:8.1f} GB/s")
     print(f"|stem - f64| on 4 clips {err:.2e}")
 
 
