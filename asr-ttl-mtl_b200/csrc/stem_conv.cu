@@ -21,9 +21,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
-#include <cstring>
-
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 
 #include "kernels.h"
 
@@ -136,6 +136,27 @@ __device__ __forceinline__ float gelu_from_half(float h) {
     return fmaf(-a, e, h + a);       // h + |h| (1 - erfc): NaN stays NaN
 }
 
+// two values at once: the same operations (and roundings) as gelu_from_half on each, as packed FMUL2 / FFMA2 / FADD2 -
+// half the issue slots of the epilogue's arithmetic
+__device__ __forceinline__ float2 gelu2_from_half(float2 h) {
+    const float2 a = make_float2(fabsf(h.x), fabsf(h.y));
+    float2 u = __fmul2_rn(a, make_float2(1.41421356237309515f, 1.41421356237309515f));
+    u.x = fminf(u.x, 4.3f);
+    u.y = fminf(u.y, 4.3f);
+    float2 q = make_float2(-5.393774335971102e-05f, -5.393774335971102e-05f);
+    q = __ffma2_rn(q, u, make_float2(0.00014493041089735925f, 0.00014493041089735925f));
+    q = __ffma2_rn(q, u, make_float2(0.0031301151029765606f, 0.0031301151029765606f));
+    q = __ffma2_rn(q, u, make_float2(-0.03049657866358757f, -0.03049657866358757f));
+    q = __ffma2_rn(q, u, make_float2(0.14962077140808105f, 0.14962077140808105f));
+    q = __ffma2_rn(q, u, make_float2(0.918138325214386f, 0.918138325214386f));
+    q = __ffma2_rn(q, u, make_float2(1.6279326677322388f, 1.6279326677322388f));
+    const float2 t = __fmul2_rn(make_float2(-u.x, -u.y), q);
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+    return __ffma2_rn(make_float2(-a.x, -a.y), e, __fadd2_rn(h, a));
+}
+
 // (clip, tile inside the clip) of a CTA's k-th tile, advanced by the grid's stride without a division
 struct TileStep { int clips, tiles, tiles_per_clip; };
 struct TileWalk {
@@ -160,7 +181,13 @@ struct StemArgs {
     int64_t batch;
     int n_frames, n_state;
     int vector_io;             // n_frames % 4 == 0 and 16-byte aligned pointers: 16-byte loads, TMA tensor stores
+    int debug;                 // measurement switches (switches build only, B200MEL_STEM_FLAGS): 1 no GELU, 2 no stores, 4 no loads
 };
+#if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
+#define STEM_DEBUG(bit) ((a.debug & (bit)) != 0)
+#else
+#define STEM_DEBUG(bit) false
+#endif
 
 // clamp of audio.py:155 in the (x + 4) / 4 domain, then TF32
 // (max.NaN keeps a NaN of either side, like torch.maximum; the tensor core drops the low 13 bits of what it reads, so
@@ -285,7 +312,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float* p = src + item_src[r];
-                    const bool load = (r < 2 || third) && !silent && t0 + item_f[r] < a.n_frames;
+                    const bool load = (r < 2 || third) && !silent && t0 + item_f[r] < a.n_frames && !STEM_DEBUG(4);
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
                         v[r][m] = silent ? make_float4(-1.5f, -1.5f, -1.5f, -1.5f) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -390,9 +417,14 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                     if (lane == 0) mbar_arrive(&bars.d_empty[buf]);
                 }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) d[i] = gelu_from_half(fmaf(d[i], 0.5f, half_bias));
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 h = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(0.5f, 0.5f), make_float2(half_bias, half_bias));
+                    const float2 g = STEM_DEBUG(1) ? h : gelu2_from_half(h);
+                    d[i] = g.x;
+                    d[i + 1] = g.y;
+                }
                 const int t = t0 + piece * 32;
-                if (t >= a.n_frames) continue;                    // (warp-uniform)
+                if (t >= a.n_frames || STEM_DEBUG(2)) continue;   // (warp-uniform)
                 if (a.vector_io) {
                     // the staging piece used two stores ago must have been read by the TMA unit
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -474,7 +506,10 @@ cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, c
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
             vector_io = 1;
     }
-    StemArgs a{mel, max_keys, tile_keys, global_max, weight, bias, out, batch, n_frames, n_state, vector_io};
+    StemArgs a{mel, max_keys, tile_keys, global_max, weight, bias, out, batch, n_frames, n_state, vector_io, 0};
+#if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
+    if (std::getenv("B200MEL_STEM_FLAGS") != nullptr) a.debug = std::atoi(std::getenv("B200MEL_STEM_FLAGS"));
+#endif
     ProfileScope profile(3, stream);
     stem_conv1_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kStemThreads, kStemSmem, stream>>>(a, out_map);
     count_launch();
