@@ -992,6 +992,7 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
             if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 1);
             // (the quadrant's three warps read the same rows: the same answer, no exchange)
             const bool quad_zero = (known_zero || quadrant_is_silent(quad_rows, fr, part, lane, quad, info.probe[quad])) && !TC_DEBUG_FLAG(0x10000);
+            if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 8);
             const int release_sweep = quad_zero ? 0 : 1;   // the pass after which this warp no longer reads the half's rows
             uint32_t scale = last_scale;
 #pragma unroll 1
