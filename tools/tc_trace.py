@@ -29,9 +29,15 @@ if not os.environ.get("B200MEL_TC_TRACE"):
     for i in range(20):
         b.log_mel_spectrogram_batch(x[i & 1], n_mels=n_mels, variant="tcgen05", out=y)
     torch.cuda.synchronize()
-    _native.profile_enable(True); _native.profile_collect()
-    for i in range(200):
-        b.log_mel_spectrogram_batch(x[i & 1], n_mels=n_mels, variant="tcgen05", out=y)
-    torch.cuda.synchronize()
-    ms, n = _native.profile_collect()["tcgen05_pass"]
-    print(f"flags={os.environ.get('B200MEL_TC_FLAGS', '0')} n_mels={n_mels} pcm={bool(os.environ.get('PCM'))}: {ms / n:.4f} ms per {B} clips (kernel events, {n} launches)")
+    # BLOCKS blocks of 200 launches (run-to-run noise on this pool is +-2 %: compare medians, not single blocks)
+    blocks = []
+    for _ in range(int(os.environ.get("BLOCKS", "1"))):
+        _native.profile_enable(True); _native.profile_collect()
+        for i in range(200):
+            b.log_mel_spectrogram_batch(x[i & 1], n_mels=n_mels, variant="tcgen05", out=y)
+        torch.cuda.synchronize()
+        ms, n = _native.profile_collect()["tcgen05_pass"]
+        blocks.append(ms / n)
+    blocks.sort()
+    extra = f" (min {blocks[0]:.4f}, median {blocks[len(blocks) // 2]:.4f}, max {blocks[-1]:.4f} over {len(blocks)} blocks)" if len(blocks) > 1 else ""
+    print(f"flags={os.environ.get('B200MEL_TC_FLAGS', '0')} n_mels={n_mels} pcm={bool(os.environ.get('PCM'))}: {blocks[len(blocks) // 2]:.4f} ms per {B} clips (kernel events, {n} launches){extra}")
