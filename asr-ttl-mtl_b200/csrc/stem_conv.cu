@@ -118,6 +118,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t t, float* d) {
     for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t t, float* d) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(t) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(r[i]);
+}
+
 // GELU(v) = v Phi(v) = h + |h| erf(|h| sqrt 2), h = v / 2, with erfc(u) = 2^(-u q(u)) on [0, 4.3] (beyond: < 2e-9):
 // q a degree-6 fit (tools/fit_gelu.py: |erfc error| 4.5e-7, |GELU error| <= 8.2e-8 for every v - below float32's spacing
 // at 1) - one MUFU and nine FMA-pipe instructions instead of erff's two dozen.  `h` = half the pre-activation.
@@ -406,34 +417,55 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
             mbar_wait_relaxed(&bars.d_full[buf], parity, 100);
             parity ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int piece = 0; piece < kStemTile / 32; ++piece) {
-                float d[32];
-                tmem_ld32(d_addr + piece * 32, d);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (piece == kStemTile / 32 - 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars.d_empty[buf]);
-                }
+            // The accumulator comes in half pieces of 16 frames through two sets of registers: the next half piece's tcgen05.ld is
+            // in flight while this one goes through the GELU; two half pieces make one 32 x 32 store.
+            auto activate = [&](float (&d)[16]) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
+                for (int i = 0; i < 16; i += 2) {
                     const float2 h = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(0.5f, 0.5f), make_float2(half_bias, half_bias));
                     const float2 g = STEM_DEBUG(1) ? h : gelu2_from_half(h);
                     d[i] = g.x;
                     d[i + 1] = g.y;
                 }
+            };
+            auto stage = [&](const float (&d)[16], uint32_t dst, int half_piece) {   // 16 frames = chunks 4 h .. 4 h + 3 of the 128-byte row
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((4 * half_piece + j) << 4) ^ swizzle)), "f"(d[4 * j]),
+                                 "f"(d[4 * j + 1]), "f"(d[4 * j + 2]), "f"(d[4 * j + 3]) : "memory");
+            };
+            float da[16], db[16];
+            tmem_ld16(d_addr, da);
+#pragma unroll 1
+            for (int piece = 0; piece < kStemTile / 32; ++piece) {
                 const int t = t0 + piece * 32;
-                if (t >= a.n_frames || STEM_DEBUG(2)) continue;   // (warp-uniform)
-                if (a.vector_io) {
+                const bool store = t < a.n_frames && !STEM_DEBUG(2);   // (warp-uniform)
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");            // da: frames 32 p .. + 15
+                tmem_ld16(d_addr + piece * 32 + 16, db);
+                activate(da);
+                uint32_t dst = 0;
+                if (store && a.vector_io) {
                     // the staging piece used two stores ago must have been read by the TMA unit
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
-                    const uint32_t dst = piece_base + (pieces_out & 1) * kStemPieceBytes;
+                    dst = piece_base + (pieces_out & 1) * kStemPieceBytes;
+                    stage(da, dst, 0);
+                } else if (store) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j << 4) ^ swizzle)), "f"(d[4 * j]), "f"(d[4 * j + 1]),
-                                     "f"(d[4 * j + 2]), "f"(d[4 * j + 3]) : "memory");
+                    for (int i = 0; i < 16; ++i)
+                        if (t + i < a.n_frames) out[piece * 32 + i] = da[i];
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");            // db: frames 32 p + 16 .. + 31
+                if (piece + 1 < kStemTile / 32) {
+                    tmem_ld16(d_addr + (piece + 1) * 32, da);
+                } else {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.d_empty[buf]);   // the whole accumulator is in registers
+                }
+                activate(db);
+                if (store && a.vector_io) {
+                    stage(db, dst, 1);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
@@ -443,10 +475,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++pieces_out;
-                } else {
+                } else if (store) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (t + i < a.n_frames) out[piece * 32 + i] = d[i];
+                    for (int i = 0; i < 16; ++i)
+                        if (t + 16 + i < a.n_frames) out[piece * 32 + 16 + i] = db[i];
                 }
             }
         }
