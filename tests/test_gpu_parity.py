@@ -563,3 +563,20 @@ def test_front_end_call_can_be_captured_in_a_cuda_graph(b200):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, b200.log_mel_spectrogram_batch(x))
+
+
+def test_one_max_per_call_with_zero_padded_rows(b200):
+    """The reference's 2-D semantics (ONE max over the call, audio.py:155) on a batch whose rows have zero tails and one row of
+    nothing but zeros: the tiles of silence (not stored by the front-end, filled by the finish kernel) take the CALL's clamp."""
+    n = 16000 * 8
+    rows = np.zeros((5, n), dtype=np.float32)
+    rows[0] = signals.make_signal("gauss", n, 1)
+    rows[1, : n // 2] = 0.01 * signals.make_signal("gauss", n // 2, 2)
+    rows[2, :1000] = signals.make_signal("uniform", 1000, 3)
+    rows[4, : n - 7] = 3.0 * signals.make_signal("gauss", n - 7, 4)
+    got = b200.log_mel_spectrogram(torch.from_numpy(rows), device=DEV)
+    want = orc.logmel_f32_port(rows, 80)
+    assert tuple(got.shape) == (5, 80, n // 160)
+    assert _maxerr(got, want) <= TOL
+    assert torch.all(got[3] == got[3].flatten()[0])      # the silent row sits on the call's max - 8 clamp
+    assert abs(float(got.max() - got[3].flatten()[0]) - 2.0) < 1e-6
