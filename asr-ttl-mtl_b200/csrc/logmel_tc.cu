@@ -896,14 +896,24 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         mbar_init(&bars.d_empty, 4);
         s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first tile's two halves are on their way while the CTA fetches its matrices (nothing has touched the audio
+        // buffers yet; their pad words are never read, so they need no initialisation)
+        if (static_cast<int64_t>(blockIdx.x) < total_tiles) {
+            const TileCursor first(tiles_per_clip);
+            const int64_t valid = valid_from(a, length_of(a, first.at.clip));
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                float* s_half = s_audio + h * (kTcHalfStride / 4);
+                const int mode = half_mode<InT>(a, tma_rows, first.at, h, valid);
+                if (mode == kModeTma) tma_load_half(&audio_map, first.at, h, s_half, &bars.audio_full[h]);
+                else if (mode == kModePcm) pcm_load_half(a, first.at, h, s_half, &bars.audio_full[h]);
+            }
+        }
     }
     {
         const uint4* src = reinterpret_cast<const uint4*>(operands);
         uint4* dst = reinterpret_cast<uint4*>(smem_raw + kSmemOperands);
         for (int i = tid; i < kTcOperandBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
-        // the audio buffers start as zeros: the pad words of a row are never written by the cooperative loaders
-        uint4* za = reinterpret_cast<uint4*>(smem_raw + kSmemAudio);
-        for (int i = tid; i < (kTcHalfStride + kTcHalfBytes) / 16; i += kTcThreads) za[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core / TMA (async proxy) accesses
     tc_fence_before();
@@ -952,10 +962,9 @@ logmel_tc_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ C
         // the utterance lengths of this tile, the next one and the one after (the tiles whose copy / L2 prefetch this one issues)
         int32_t len_cur = length_of(a, cursor.at.clip), len_next = length_of(a, cursor.peek_next().clip),
                 len_after = length_of(a, cursor.next_of(cursor.peek_next()).clip);
-        if (part == 0 && (quad & 1) == 0 && lane == 0 && static_cast<int64_t>(blockIdx.x) < total_tiles) {   // warps 0 and 2
-            issue_half(cursor.at, valid_from(a, len_cur));
-            if (static_cast<int64_t>(blockIdx.x) + gridDim.x < total_tiles) prefetch_half(cursor.peek_next(), valid_from(a, len_next));
-        }
+        // (the first tile's copy was issued at the top of the kernel; one thread per half asks L2 for the second tile)
+        if (part == 0 && (quad & 1) == 0 && lane == 0 && static_cast<int64_t>(blockIdx.x) + gridDim.x < total_tiles)   // warps 0 and 2
+            prefetch_half(cursor.peek_next(), valid_from(a, len_next));
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, cursor.advance()) {
             if (quad == 0) TC_TRACE(part == 2 ? 5 : 1 + part, ti, 0);
             const TileCoord tcl = cursor.at;
