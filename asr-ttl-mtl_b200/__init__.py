@@ -24,4 +24,4 @@ from .audio import (  # noqa: F401
 )
 from .install import install, uninstall  # noqa: F401
 from .sharding import shard_range  # noqa: F401
-from .stem import encoder_stem, log_mel_encoder_stem  # noqa: F401
+from .stem import encoder_stem, encoder_stem2, log_mel_encoder_stem, log_mel_encoder_stem2, pack_conv2_weight  # noqa: F401

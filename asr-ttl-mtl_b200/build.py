@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200mel.so")
 
-SOURCES = ["b200mel_api.cu", "logmel_fft.cu", "logmel_tc.cu", "stem_conv.cu", "mel_windows.cu"]
+SOURCES = ["b200mel_api.cu", "logmel_fft.cu", "logmel_tc.cu", "stem_conv.cu", "stem_conv2.cu", "mel_windows.cu"]
 HEADERS = ["kernels.h", "logmel_core.cuh", "tables.h", "tc_core.cuh", "tc_tables.h", "mel_bands.h", os.path.join(ROOT, "include", "b200mel.h")]
 
 NVCC_FLAGS = [

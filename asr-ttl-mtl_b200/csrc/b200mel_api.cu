@@ -304,19 +304,46 @@ int b200mel_logmel_device(const b200mel_plan* plan, const void* audio, int dtype
     return B200MEL_OK;
 }
 
-int b200mel_stem_conv1_gelu_device(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels,
-                                   int64_t n_frames, const float* weight, const float* bias, int n_state, float* out,
-                                   void* stream) {
-    if (mel == nullptr || weight == nullptr || bias == nullptr || out == nullptr) return B200MEL_ERR_NULL_POINTER;
+namespace {
+int stem_conv1(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels, int64_t n_frames, const float* weight,
+               const float* bias, int n_state, float* out, void* out_fm16, void* stream) {
+    if (mel == nullptr || weight == nullptr || bias == nullptr || (out == nullptr && out_fm16 == nullptr)) return B200MEL_ERR_NULL_POINTER;
     if (n_mels != 80) return B200MEL_ERR_BAD_N_MELS;
-    if (batch < 0 || n_frames < 0 || n_frames > 0x7fffffff || n_state <= 0 || n_state % 128 != 0 || n_state > 128 * 148)
+    if (batch < 0 || n_frames < 0 || n_frames > 0x7ffffff0 || n_state <= 0 || n_state % 128 != 0 || n_state > 128 * 148)
         return B200MEL_ERR_BAD_ARGUMENT;
     const uint32_t* keys = static_cast<const uint32_t*>(workspace);
     const uint32_t* tile_keys = nullptr;
     if (keys != nullptr && (flags & B200MEL_FLAG_TILE_KEYS))
         tile_keys = reinterpret_cast<const uint32_t*>(static_cast<const char*>(workspace) + b200mel_workspace_bytes(batch));
     B200_CUDA(launch_stem_conv1_gelu(mel, keys, tile_keys, (flags & B200MEL_FLAG_GLOBAL_MAX) ? 1 : 0, batch, static_cast<int>(n_frames),
-                                     weight, bias, n_state, out, static_cast<cudaStream_t>(stream)));
+                                     weight, bias, n_state, out, out_fm16, static_cast<cudaStream_t>(stream)));
+    return B200MEL_OK;
+}
+}  // namespace
+
+int b200mel_stem_conv1_gelu_device(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels,
+                                   int64_t n_frames, const float* weight, const float* bias, int n_state, float* out,
+                                   void* stream) {
+    if (out == nullptr) return B200MEL_ERR_NULL_POINTER;
+    return stem_conv1(mel, workspace, flags, batch, n_mels, n_frames, weight, bias, n_state, out, nullptr, stream);
+}
+
+int b200mel_stem_conv1_gelu_fm16_device(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels,
+                                        int64_t n_frames, const float* weight, const float* bias, int n_state, void* out_fm16,
+                                        void* stream) {
+    if (out_fm16 == nullptr) return B200MEL_ERR_NULL_POINTER;
+    return stem_conv1(mel, workspace, flags, batch, n_mels, n_frames, weight, bias, n_state, nullptr, out_fm16, stream);
+}
+
+int b200mel_stem_conv2_gelu_device(const void* h_fm16, int64_t batch, int64_t frames_padded, const void* weight_f16, const float* bias,
+                                   const float* positional_embedding, int n_state, float* out, void* stream) {
+    if (h_fm16 == nullptr || weight_f16 == nullptr || bias == nullptr || out == nullptr) return B200MEL_ERR_NULL_POINTER;
+    if (batch < 0 || frames_padded < 0 || frames_padded % 2 != 0 || frames_padded > 0x7ffffff0 || n_state <= 0 || n_state % 128 != 0 ||
+        n_state > 128 * 148 || batch > 0x7fffffff)
+        return B200MEL_ERR_BAD_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(h_fm16) | reinterpret_cast<uintptr_t>(weight_f16)) % 16 != 0) return B200MEL_ERR_BAD_ARGUMENT;
+    B200_CUDA(launch_stem_conv2_gelu(h_fm16, batch, static_cast<int>(frames_padded), weight_f16, bias, positional_embedding, n_state, out,
+                                     static_cast<cudaStream_t>(stream)));
     return B200MEL_OK;
 }
 

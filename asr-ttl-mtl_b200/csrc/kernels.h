@@ -54,8 +54,16 @@ cudaError_t launch_normalise(float* out, const uint32_t* max_keys, int64_t batch
 
 // Encoder stem (stem_conv.cu): out = gelu(conv1d(x, weight, bias, kernel 3, padding 1)), x = mel clamped at max - 8 on
 // load when max_keys is given (then mel is the front-end's output before launch_tc_finish).  n_mels 80, n_state % 128 == 0.
+// out_fm16 != nullptr: the result goes there instead, as half [batch, n_frames rounded up to even, n_state] - frames major,
+// the operand layout of launch_stem_conv2_gelu (`out` is not used).
 cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, const uint32_t* tile_keys, int global_max, int64_t batch,
-                                   int n_frames, const float* weight, const float* bias, int n_state, float* out, cudaStream_t stream);
+                                   int n_frames, const float* weight, const float* bias, int n_state, float* out, void* out_fm16, cudaStream_t stream);
+
+// Encoder stem, second layer (stem_conv2.cu): out[b, t, n] = gelu(conv1d(h, weight, bias, kernel 3, stride 2, padding 1))[b, n, t]
+// (+ pos[t, n]), t < frames_padded / 2.  h_fm16: half [batch, frames_padded (even), n_state] as launch_stem_conv1_gelu leaves
+// it; weight_f16: half [3, n_state, n_state] (tap, out, in); n_state % 128 == 0.
+cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames_padded, const void* weight_f16, const float* bias, const float* pos,
+                                   int n_state, float* out, cudaStream_t stream);
 
 // Window cut behind the front-end (mel_windows.cu): out[w, m, j] = mel[m, seeks[w] + j] for j < sizes[w] (nullptr: the whole
 // window), zeros behind - transcribe.py:282-286 for n_windows windows at once, float32 or half.

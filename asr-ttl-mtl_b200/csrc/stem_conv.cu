@@ -19,6 +19,7 @@
 // clamp, TF32 rounding, 4 x 4 register transpose, 16-byte shared stores; a tile's loads are issued before the wait for
 // its stage, the next tile's lines are asked from L2).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -189,6 +190,8 @@ struct StemArgs {
     const float* weight;       // [n_state, 80, 3] (torch Conv1d layout)
     const float* bias;         // [n_state]
     float* out;                // [batch, n_state, n_frames]
+    __half* out_fm;            // frame-major variant: half [batch, fm_frames, n_state], the operand layout of conv2 (stem_conv2.cu)
+    int fm_frames;             // its frames per clip (n_frames rounded up to even)
     int64_t batch;
     int n_frames, n_state;
     int vector_io;             // n_frames % 4 == 0 and 16-byte aligned pointers: 16-byte loads, TMA tensor stores
@@ -209,6 +212,7 @@ __device__ __forceinline__ uint32_t stem_input(float y, float floor_y) {
     return __float_as_uint(m) + (fabsf(m) < __uint_as_float(0x7f800000u) ? 0x1000u : 0u);
 }
 
+template <bool kFm>
 __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const StemArgs a, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* const smem_raw = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
@@ -447,7 +451,15 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                 tmem_ld16(d_addr + piece * 32 + 16, db);
                 activate(da);
                 uint32_t dst = 0;
-                if (store && a.vector_io) {
+                if constexpr (kFm) {
+                    // frame-major half: a frame's 32 channels of this warp are 64 contiguous bytes
+                    if (store) {
+                        __half* fm = a.out_fm + ((static_cast<int64_t>(w.clip) * a.fm_frames + t) * a.n_state + slice * kStemN + n);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (t + i < a.n_frames) fm[static_cast<int64_t>(i) * a.n_state] = __float2half_rn(da[i]);
+                    }
+                } else if (store && a.vector_io) {
                     // the staging piece used two stores ago must have been read by the TMA unit
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
@@ -467,7 +479,14 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                     if (lane == 0) mbar_arrive(&bars.d_empty[buf]);   // the whole accumulator is in registers
                 }
                 activate(db);
-                if (store && a.vector_io) {
+                if constexpr (kFm) {
+                    if (store) {
+                        __half* fm = a.out_fm + ((static_cast<int64_t>(w.clip) * a.fm_frames + t + 16) * a.n_state + slice * kStemN + n);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (t + 16 + i < a.n_frames) fm[static_cast<int64_t>(i) * a.n_state] = __float2half_rn(db[i]);
+                    }
+                } else if (store && a.vector_io) {
                     stage(db, dst, 1);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -495,7 +514,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
 }  // namespace
 
 cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, const uint32_t* tile_keys, int global_max, int64_t batch, int n_frames, const float* weight,
-                                   const float* bias, int n_state, float* out, cudaStream_t stream) {
+                                   const float* bias, int n_state, float* out, void* out_fm16, cudaStream_t stream) {
     if (batch <= 0 || n_frames <= 0) return cudaSuccess;
     constexpr int kMaxDevices = 64;
     static int sms_by_device[kMaxDevices] = {0};                      // (also: the kernel's attributes are set on this device)
@@ -504,7 +523,8 @@ cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, c
     if (err != cudaSuccess) return err;
     if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
     if (sms_by_device[device] == 0) {
-        err = cudaFuncSetAttribute(stem_conv1_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
+        err = cudaFuncSetAttribute(stem_conv1_gelu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(stem_conv1_gelu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
         int count = 0;
         if (err == cudaSuccess) err = cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device);
         if (err != cudaSuccess) return err;
@@ -522,7 +542,9 @@ cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, c
     CUtensorMap out_map;
     std::memset(&out_map, 0, sizeof(out_map));
     int vector_io = 0;
-    if (n_frames % 4 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+    if (out_fm16 != nullptr) {
+        vector_io = n_frames % 4 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0;   // (the loads only: this variant stores by itself)
+    } else if (n_frames % 4 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
         batch * n_state < (int64_t{1} << 31)) {
         using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -541,12 +563,13 @@ cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, c
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
             vector_io = 1;
     }
-    StemArgs a{mel, max_keys, tile_keys, global_max, weight, bias, out, batch, n_frames, n_state, vector_io, 0};
+    StemArgs a{mel, max_keys, tile_keys, global_max, weight, bias, out, static_cast<__half*>(out_fm16), n_frames + (n_frames & 1), batch, n_frames, n_state, vector_io, 0};
 #if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
     if (std::getenv("B200MEL_STEM_FLAGS") != nullptr) a.debug = std::atoi(std::getenv("B200MEL_STEM_FLAGS"));
 #endif
     ProfileScope profile(3, stream);
-    stem_conv1_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kStemThreads, kStemSmem, stream>>>(a, out_map);
+    if (out_fm16 != nullptr) stem_conv1_gelu_kernel<true><<<static_cast<unsigned>(walkers * slices), kStemThreads, kStemSmem, stream>>>(a, out_map);
+    else stem_conv1_gelu_kernel<false><<<static_cast<unsigned>(walkers * slices), kStemThreads, kStemSmem, stream>>>(a, out_map);
     count_launch();
     return cudaGetLastError();
 }

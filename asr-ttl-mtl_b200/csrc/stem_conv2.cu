@@ -1,0 +1,324 @@
+// Encoder stem, second layer: conv2 (kernel 3, stride 2, padding 1) + GELU, the move to [batch, frames, channels] and the
+// positional embedding of Whisper's AudioEncoder (reference whisper/model.py:180, :194-197):
+//
+//   out[b, t, n] = gelu(bias[n] + sum_{c, k} W[n, c, k] h[b, c, 2 t + k - 1]) (+ pos[t, n]),   h[.., -1] = h[.., T] = 0
+//
+// as a GEMM on the tcgen05 tensor cores, D[128 channels, 256 frames] += W_k[128, 64 c] H_k[64 c, 256 frames] over the three
+// taps and n_state / 64 channel chunks (K = 3 n_state), kind::f16: the operands are IEEE half - the same 11-bit
+// significand TF32 has, i.e. the operand precision of torch's own convolution on this GPU (allow_tf32, cudnn's default)
+// and of the reference's fp16 inference (transcribe.py:127) - with float32 accumulation in tensor memory.
+//
+// The first layer (stem_conv.cu, frame-major variant) leaves h as half [batch, frames, channels]: channels contiguous =
+// K-major, so a tap's operand is ONE TMA tensor copy.  Viewed as [batch, frames / 2, parity, channels], tap k of output
+// frame t is row (t - 1, odd), (t, even), (t, odd): the stride-2 convolution needs no im2col and no strided descriptor, and
+// the zero padding in front of the clip is the copy's out-of-bounds fill.  The weights come as half [3, n_state, n_state]
+// (tap, out channel, in channel: packed once by the host mirror), also one tensor copy per stage.
+//
+// One persistent CTA per SM, 10 warps: 8 epilogue (thread = channel; two warps per tensor-memory lane quadrant, 128 frames
+// each: bias, GELU, positional embedding, 128-byte row stores - a frame's 32 channels are one line), 1 MMA issue, 1 TMA
+// producer.  Four stages of 48 KB (A 128 x 64, B 256 x 64, 128-byte swizzle), two accumulators of 256 columns: the
+// epilogue of a tile overlaps the MMAs of the next.  CTAs with the other 128-channel slices walk the same tiles at the same
+// time, so h comes from HBM once.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace b200mel {
+
+namespace {
+
+constexpr int kC2M = 128;                        // out channels per CTA = MMA M = TMEM lanes
+constexpr int kC2N = 256;                        // output frames per tile = MMA N
+constexpr int kC2K = 64;                         // in channels per stage: 128 bytes of half = one swizzle row
+constexpr int kC2Stages = 4;
+constexpr int kC2ABytes = kC2M * 128, kC2BBytes = kC2N * 128, kC2StageBytes = kC2ABytes + kC2BBytes;   // 16 + 32 KB
+constexpr int kC2Smem = kC2Stages * kC2StageBytes + 1024;                                              // + slack to align the base
+constexpr int kC2EpiWarps = 8, kC2WarpMma = 8, kC2WarpTma = 9, kC2Threads = 10 * 32;
+constexpr uint32_t kC2Idesc = (1u << 4) | (static_cast<uint32_t>(kC2N >> 3) << 17) | (static_cast<uint32_t>(kC2M >> 4) << 24);   // f16 x f16 -> f32, K-major
+static_assert(kC2Smem <= 227 * 1024, "shared memory layout");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// (a protocol bug ends the kernel with garbage instead of hanging the device)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned sleep_ns) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done || ++spins > (1u << 22)) break;
+        if (sleep_ns) __nanosleep(sleep_ns);
+    }
+}
+// K-major operand with 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+    return (uint64_t{2} << 61) | (uint64_t{1} << 46) | (uint64_t{1024 >> 4} << 32) | (uint64_t{1} << 16) | ((smem_addr & 0x3ffffu) >> 4);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, bool accumulate) {
+    asm volatile("{\n.reg .pred Q;\nsetp.ne.u32 Q, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, Q;\n}\n"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kC2Idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t t, float* d) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(t) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(r[i]);
+}
+
+// GELU(v) = v Phi(v) = h + |h| erf(|h| sqrt 2), h = v / 2: the degree-6 fit of stem_conv.cu (tools/fit_gelu.py,
+// |GELU error| <= 8.2e-8), two values at once as packed FMUL2 / FFMA2 / FADD2
+__device__ __forceinline__ float2 gelu2_from_half(float2 h) {
+    const float2 a = make_float2(fabsf(h.x), fabsf(h.y));
+    float2 u = __fmul2_rn(a, make_float2(1.41421356237309515f, 1.41421356237309515f));
+    u.x = fminf(u.x, 4.3f);
+    u.y = fminf(u.y, 4.3f);
+    float2 q = make_float2(-5.393774335971102e-05f, -5.393774335971102e-05f);
+    q = __ffma2_rn(q, u, make_float2(0.00014493041089735925f, 0.00014493041089735925f));
+    q = __ffma2_rn(q, u, make_float2(0.0031301151029765606f, 0.0031301151029765606f));
+    q = __ffma2_rn(q, u, make_float2(-0.03049657866358757f, -0.03049657866358757f));
+    q = __ffma2_rn(q, u, make_float2(0.14962077140808105f, 0.14962077140808105f));
+    q = __ffma2_rn(q, u, make_float2(0.918138325214386f, 0.918138325214386f));
+    q = __ffma2_rn(q, u, make_float2(1.6279326677322388f, 1.6279326677322388f));
+    const float2 t = __fmul2_rn(make_float2(-u.x, -u.y), q);
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+    return __ffma2_rn(make_float2(-a.x, -a.y), e, __fadd2_rn(h, a));
+}
+
+struct C2Barriers { uint64_t full[kC2Stages], empty[kC2Stages], d_full[2], d_empty[2]; };
+
+struct C2Args {
+    const float* bias;     // [n_state]
+    const float* pos;      // [frames_out, n_state] or nullptr
+    float* out;            // [batch, frames_out, n_state]
+    int64_t batch;
+    int frames_out, n_state;
+};
+
+__global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2Args a, const __grid_constant__ CUtensorMap w_map,
+                                                                        const __grid_constant__ CUtensorMap h_map) {
+    extern __shared__ unsigned char smem_unaligned[];
+    unsigned char* const smem_raw = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
+    __shared__ __align__(8) C2Barriers bars;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    const int slices = a.n_state / kC2M;
+    const int slice = blockIdx.x % slices;                       // this CTA's 128 out channels
+    const int walkers = gridDim.x / slices;                      // CTAs that share the tiles of a slice
+    const int walker = blockIdx.x / slices;
+    const int tiles_per_clip = (a.frames_out + kC2N - 1) / kC2N;
+    const int64_t total_tiles = a.batch * tiles_per_clip;
+    const int my_tiles = walker < total_tiles ? static_cast<int>((total_tiles - walker + walkers - 1) / walkers) : 0;
+    const int k_chunks = a.n_state / kC2K;                       // stages per tile = 3 k_chunks
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < kC2Stages; ++i) {
+            mbar_init(&bars.full[i], 1);         // the producer's arrive.expect_tx
+            mbar_init(&bars.empty[i], 1);        // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.d_full[i], 1);       // tcgen05.commit
+            mbar_init(&bars.d_empty[i], kC2EpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp == kC2WarpTma) {
+        // ===== producer: per stage the weights' box (tap, slice, 64 in channels) and the tap's 256 rows of h =====
+        if (lane == 0) {
+            uint32_t parity = 1;                                 // empty: the first use of a stage passes
+            int stage = 0;
+            for (int k = 0; k < my_tiles; ++k) {
+                const int64_t tile = walker + static_cast<int64_t>(k) * walkers;
+                const int clip = static_cast<int>(tile / tiles_per_clip);
+                const int t0 = static_cast<int>(tile % tiles_per_clip) * kC2N;
+                for (int j = 0; j < k_chunks; ++j) {
+                    for (int tap = 0; tap < 3; ++tap) {
+                        mbar_wait(&bars.empty[stage], parity, 32);
+                        unsigned char* sa = smem_raw + stage * kC2StageBytes;
+                        const uint32_t bar = smem_u32(&bars.full[stage]);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kC2StageBytes) : "memory");
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                     ::"r"(smem_u32(sa)), "l"(&w_map), "r"(j * kC2K), "r"(slice * kC2M), "r"(tap), "r"(bar) : "memory");
+                        // input frame 2 t + tap - 1 = (row t - 1, odd), (row t, even), (row t, odd); row -1 is filled with zeros
+                        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                                     ::"r"(smem_u32(sa + kC2ABytes)), "l"(&h_map), "r"(j * kC2K), "r"(tap == 1 ? 0 : 1), "r"(tap == 0 ? t0 - 1 : t0),
+                                       "r"(clip), "r"(bar) : "memory");
+                        if (++stage == kC2Stages) { stage = 0; parity ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == kC2WarpMma) {
+        // ===== MMA issue: 4 MMAs of K 16 per stage =====
+        if (lane == 0) {
+            uint32_t full_parity = 0, d_parity = 1;              // d_empty: the first two waits pass
+            int stage = 0, buf = 0;
+            const uint32_t base = smem_u32(smem_raw);
+            for (int k = 0; k < my_tiles; ++k) {
+                mbar_wait(&bars.d_empty[buf], d_parity, 32);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + buf * kC2N;
+                for (int s = 0; s < 3 * k_chunks; ++s) {
+                    mbar_wait(&bars.full[stage], full_parity, 0);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t a_desc = sw128_desc(base + stage * kC2StageBytes);
+                    const uint64_t b_desc = sw128_desc(base + stage * kC2StageBytes + kC2ABytes);
+#pragma unroll
+                    for (int i = 0; i < kC2K / 16; ++i)          // K 16 = 32 bytes further inside the 128-byte row
+                        mma_f16_ss(d_tmem, a_desc + 2 * i, b_desc + 2 * i, s + i > 0);
+                    mma_commit(&bars.empty[stage]);
+                    if (++stage == kC2Stages) { stage = 0; full_parity ^= 1u; }
+                }
+                mma_commit(&bars.d_full[buf]);
+                buf ^= 1;
+                if (buf == 0) d_parity ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue: thread = channel; warp w takes lane quadrant w % 4 and frames 128 (w / 4) .. + 127 of the tile =====
+        const int quadrant = warp & 3, part = warp >> 2;
+        const int n = slice * kC2M + quadrant * 32 + lane;
+        const float half_bias = 0.5f * __ldg(a.bias + n);
+        uint32_t parities = 0;                                   // bit b: the parity of d_full[b] to wait for
+        for (int k = 0; k < my_tiles; ++k) {
+            const int buf = k & 1;
+            const int64_t tile = walker + static_cast<int64_t>(k) * walkers;
+            const int clip = static_cast<int>(tile / tiles_per_clip);
+            const int t0 = static_cast<int>(tile % tiles_per_clip) * kC2N + part * 128;
+            const uint32_t d_addr = tmem + (static_cast<uint32_t>(quadrant * 32) << 16) + buf * kC2N + part * 128;
+            float* out = a.out + ((static_cast<int64_t>(clip) * a.frames_out + t0) * a.n_state + n);
+            const float* pos = a.pos != nullptr ? a.pos + (static_cast<int64_t>(t0) * a.n_state + n) : nullptr;
+            mbar_wait(&bars.d_full[buf], (parities >> buf) & 1u, 100);
+            parities ^= 1u << buf;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int piece = 0; piece < 4; ++piece) {
+                float d[32];
+                tmem_ld32(d_addr + piece * 32, d);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (piece == 3) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.d_empty[buf]);   // the warp's part of the accumulator is in registers
+                }
+                const int t = t0 + piece * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 h = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(0.5f, 0.5f), make_float2(half_bias, half_bias));
+                    float2 g = gelu2_from_half(h);
+                    if (t + i < a.frames_out) {
+                        if (pos != nullptr) g.x += __ldg(pos + static_cast<int64_t>(piece * 32 + i) * a.n_state);
+                        out[static_cast<int64_t>(piece * 32 + i) * a.n_state] = g.x;
+                    }
+                    if (t + i + 1 < a.frames_out) {
+                        if (pos != nullptr) g.y += __ldg(pos + static_cast<int64_t>(piece * 32 + i + 1) * a.n_state);
+                        out[static_cast<int64_t>(piece * 32 + i + 1) * a.n_state] = g.y;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn tensor_map_encoder() {
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    return encode;
+}
+
+}  // namespace
+
+cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames_padded, const void* weight_f16, const float* bias, const float* pos,
+                                   int n_state, float* out, cudaStream_t stream) {
+    const int frames_out = frames_padded / 2;
+    if (batch <= 0 || frames_out <= 0) return cudaSuccess;
+    constexpr int kMaxDevices = 64;
+    static int sms_by_device[kMaxDevices] = {0};                      // (also: the kernel's attributes are set on this device)
+    int device = 0;
+    cudaError_t err = cudaGetDevice(&device);
+    if (err != cudaSuccess) return err;
+    if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (sms_by_device[device] == 0) {
+        err = cudaFuncSetAttribute(stem_conv2_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2Smem);
+        int count = 0;
+        if (err == cudaSuccess) err = cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device);
+        if (err != cudaSuccess) return err;
+        sms_by_device[device] = count;
+    }
+    const EncodeFn encode = tensor_map_encoder();
+    if (encode == nullptr) return cudaErrorNotSupported;
+    const uint64_t c = static_cast<uint64_t>(n_state);
+    CUtensorMap w_map, h_map;
+    std::memset(&w_map, 0, sizeof(w_map));
+    std::memset(&h_map, 0, sizeof(h_map));
+    {   // weights: half [3 taps][n_state out][n_state in]; box = 64 in channels x 128 out channels of one tap
+        const cuuint64_t dims[3] = {c, c, 3};
+        const cuuint64_t strides[2] = {c * 2, c * c * 2};
+        const cuuint32_t box[3] = {kC2K, kC2M, 1};
+        const cuuint32_t elem[3] = {1, 1, 1};
+        if (encode(&w_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(weight_f16), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    {   // h: half [batch][frames_padded / 2][parity][n_state]; box = 64 channels x 256 rows of one parity
+        const cuuint64_t dims[4] = {c, 2, static_cast<cuuint64_t>(frames_out), static_cast<cuuint64_t>(batch)};
+        const cuuint64_t strides[3] = {c * 2, c * 4, static_cast<cuuint64_t>(frames_padded) * c * 2};
+        const cuuint32_t box[4] = {kC2K, 1, kC2N, 1};
+        const cuuint32_t elem[4] = {1, 1, 1, 1};
+        if (encode(&h_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(h_fm16), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    const int sms = sms_by_device[device];
+    const int slices = n_state / kC2M;
+    const int64_t tiles = batch * ((frames_out + kC2N - 1) / kC2N);
+    int64_t walkers = sms / slices;                                   // CTAs per slice; every CTA of the grid is resident
+    if (walkers < 1) walkers = 1;
+    if (walkers > tiles) walkers = tiles;
+    const C2Args a{bias, pos, out, batch, frames_out, n_state};
+    ProfileScope profile(3, stream);
+    stem_conv2_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kC2Threads, kC2Smem, stream>>>(a, w_map, h_map);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b200mel

@@ -141,6 +141,29 @@ int b200mel_stem_conv1_gelu_device(const float* mel, const void* workspace, unsi
                                    int64_t n_frames, const float* weight, const float* bias, int n_state, float* out,
                                    void* stream);
 
+/* The whole encoder stem, model.py:193-197:
+ *   x = F.gelu(conv1(mel)); x = F.gelu(conv2(x)); x = x.permute(0, 2, 1); x = x + positional_embedding
+ * conv2 = Conv1d(n_state, n_state, kernel_size=3, stride=2, padding=1) (model.py:180), in two launches.
+ *
+ * b200mel_stem_conv1_gelu_fm16_device: b200mel_stem_conv1_gelu_device with its result left for conv2 -
+ *   out_fm16   device IEEE half [batch, frames_padded, n_state], frames_padded = n_frames rounded up to even: frames
+ *              major, channels contiguous.  For an odd n_frames the caller zeroes the last frame of every clip (the
+ *              convolution's padding); the kernel writes frames < n_frames only.
+ * b200mel_stem_conv2_gelu_device: the second layer as a GEMM on the tcgen05 tensor cores, IEEE-half operands (TF32's
+ *   11-bit significand: the operand precision of torch's conv with allow_tf32 and of the reference's fp16 inference,
+ *   transcribe.py:127), float32 accumulation, exact (erf) GELU -
+ *   h_fm16     what b200mel_stem_conv1_gelu_fm16_device left (16-byte aligned)
+ *   weight_f16 device IEEE half [3, n_state, n_state] = conv2.weight.permute(2, 0, 1) (tap, out channel, in channel)
+ *   bias       device float32 [n_state]
+ *   positional_embedding  device float32 [frames_padded / 2, n_state] or NULL (model.py:197; the reference asserts
+ *              frames_padded / 2 == n_ctx = 1500)
+ *   out        device float32 [batch, frames_padded / 2, n_state] - the layout behind the permute of model.py:195 */
+int b200mel_stem_conv1_gelu_fm16_device(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels,
+                                        int64_t n_frames, const float* weight, const float* bias, int n_state, void* out_fm16,
+                                        void* stream);
+int b200mel_stem_conv2_gelu_device(const void* h_fm16, int64_t batch, int64_t frames_padded, const void* weight_f16, const float* bias,
+                                   const float* positional_embedding, int n_state, float* out, void* stream);
+
 /* The window cut of the decoding loop, transcribe.py:282-286 (and :150 with seek 0):
  *   mel_segment = pad_or_trim(mel[:, seek : seek + segment_size], N_FRAMES).to(device).to(dtype)
  * for n_windows windows of one long utterance in ONE launch, written straight into zero-padded windows.
