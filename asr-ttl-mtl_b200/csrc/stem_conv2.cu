@@ -221,8 +221,25 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
             mbar_wait(&bars.d_full[buf], (parities >> buf) & 1u, 100);
             parities ^= 1u << buf;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int last = a.frames_out - 1 - t0;              // last frame of the clip, relative to this warp's first
 #pragma unroll 1
             for (int piece = 0; piece < 4; ++piece) {
+                if (piece * 32 > last) {                         // (warp-uniform) nothing left of the clip: only the hand-over
+                    if (piece == 3) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars.d_empty[buf]);
+                    }
+                    continue;
+                }
+                // the positional embedding's 32 rows first: independent loads, in flight during the accumulator's
+                float p[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) p[i] = 0.f;
+                if (pos != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) p[i] = __ldg(pos + static_cast<int64_t>(min(piece * 32 + i, last)) * a.n_state);
+                }
                 float d[32];
                 tmem_ld32(d_addr + piece * 32, d);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -231,19 +248,21 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.d_empty[buf]);   // the warp's part of the accumulator is in registers
                 }
-                const int t = t0 + piece * 32;
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     const float2 h = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(0.5f, 0.5f), make_float2(half_bias, half_bias));
-                    float2 g = gelu2_from_half(h);
-                    if (t + i < a.frames_out) {
-                        if (pos != nullptr) g.x += __ldg(pos + static_cast<int64_t>(piece * 32 + i) * a.n_state);
-                        out[static_cast<int64_t>(piece * 32 + i) * a.n_state] = g.x;
-                    }
-                    if (t + i + 1 < a.frames_out) {
-                        if (pos != nullptr) g.y += __ldg(pos + static_cast<int64_t>(piece * 32 + i + 1) * a.n_state);
-                        out[static_cast<int64_t>(piece * 32 + i + 1) * a.n_state] = g.y;
-                    }
+                    const float2 g = gelu2_from_half(h);
+                    d[i] = g.x + p[i];
+                    d[i + 1] = g.y + p[i + 1];
+                }
+                float* o = out + static_cast<int64_t>(piece * 32) * a.n_state;
+                if (piece * 32 + 31 <= last) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[static_cast<int64_t>(i) * a.n_state] = d[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (piece * 32 + i <= last) o[static_cast<int64_t>(i) * a.n_state] = d[i];
                 }
             }
         }
