@@ -192,6 +192,7 @@ struct StemArgs {
     float* out;                // [batch, n_state, n_frames]
     __half* out_fm;            // frame-major variant: half [batch, fm_frames, n_state], the operand layout of conv2 (stem_conv2.cu)
     int fm_frames;             // its frames per clip (n_frames rounded up to even)
+    int fm_tma;                // out_map describes out_fm as [batch * fm_frames rows, n_state]: whole 32-frame pieces leave by TMA tensor store
     int64_t batch;
     int n_frames, n_state;
     int vector_io;             // n_frames % 4 == 0 and 16-byte aligned pointers: 16-byte loads, TMA tensor stores
@@ -451,9 +452,18 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                 tmem_ld16(d_addr + piece * 32 + 16, db);
                 activate(da);
                 uint32_t dst = 0;
+                const bool fm_staged = kFm && a.fm_tma && t + 32 <= a.n_frames;   // (warp-uniform) a whole piece inside the clip
                 if constexpr (kFm) {
-                    // frame-major half: a frame's 32 channels of this warp are 64 contiguous bytes
-                    if (store) {
+                    // frame-major half: a frame's 32 channels of this warp are 64 contiguous bytes.  A whole piece is staged as
+                    // [32 frames][32 channels] and leaves with one TMA tensor store; the clip's last, partial piece by itself.
+                    if (store && fm_staged) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
+                        dst = piece_base - lane * 128 + (pieces_out & 1) * kStemPieceBytes;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst + i * 64 + lane * 2), "h"(__half_as_ushort(__float2half_rn(da[i]))) : "memory");
+                    } else if (store) {
                         __half* fm = a.out_fm + ((static_cast<int64_t>(w.clip) * a.fm_frames + t) * a.n_state + slice * kStemN + n);
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
@@ -480,7 +490,19 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv1_gelu_kernel(const 
                 }
                 activate(db);
                 if constexpr (kFm) {
-                    if (store) {
+                    if (store && fm_staged) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst + (16 + i) * 64 + lane * 2), "h"(__half_as_ushort(__float2half_rn(db[i]))) : "memory");
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(&out_map), "r"(slice * kStemN + (warp & 3) * 32), "r"(w.clip * a.fm_frames + t), "r"(dst) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        ++pieces_out;
+                    } else if (store) {
                         __half* fm = a.out_fm + ((static_cast<int64_t>(w.clip) * a.fm_frames + t + 16) * a.n_state + slice * kStemN + n);
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
@@ -542,8 +564,29 @@ cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, c
     CUtensorMap out_map;
     std::memset(&out_map, 0, sizeof(out_map));
     int vector_io = 0;
+    int fm_tma = 0;
+    const int fm_frames = n_frames + (n_frames & 1);
     if (out_fm16 != nullptr) {
-        vector_io = n_frames % 4 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0;   // (the loads only: this variant stores by itself)
+        vector_io = n_frames % 4 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0;   // (the loads only)
+        // the frame-major result as the TMA unit sees it: [batch * fm_frames rows, n_state] half, boxes of 32 frames x 32 channels
+        if (reinterpret_cast<uintptr_t>(out_fm16) % 16 == 0 && batch * fm_frames < (int64_t{1} << 31)) {
+            using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            static EncodeFn encode = [] {
+                void* fn = nullptr;
+                cudaDriverEntryPointQueryResult q;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+                return reinterpret_cast<EncodeFn>(fn);
+            }();
+            const cuuint64_t dims[2] = {static_cast<cuuint64_t>(n_state), static_cast<cuuint64_t>(batch * fm_frames)};
+            const cuuint64_t strides[1] = {static_cast<cuuint64_t>(n_state) * 2};
+            const cuuint32_t box[2] = {32, 32};
+            const cuuint32_t elem[2] = {1, 1};
+            if (encode != nullptr && encode(&out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_fm16, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                fm_tma = 1;
+        }
     } else if (n_frames % 4 == 0 && reinterpret_cast<uintptr_t>(mel) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
         batch * n_state < (int64_t{1} << 31)) {
         using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -563,7 +606,7 @@ cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, c
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
             vector_io = 1;
     }
-    StemArgs a{mel, max_keys, tile_keys, global_max, weight, bias, out, static_cast<__half*>(out_fm16), n_frames + (n_frames & 1), batch, n_frames, n_state, vector_io, 0};
+    StemArgs a{mel, max_keys, tile_keys, global_max, weight, bias, out, static_cast<__half*>(out_fm16), fm_frames, fm_tma, batch, n_frames, n_state, vector_io, 0};
 #if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
     if (std::getenv("B200MEL_STEM_FLAGS") != nullptr) a.debug = std::atoi(std::getenv("B200MEL_STEM_FLAGS"));
 #endif

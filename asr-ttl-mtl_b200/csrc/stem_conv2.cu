@@ -218,10 +218,28 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
             const uint32_t d_addr = tmem + (static_cast<uint32_t>(quadrant * 32) << 16) + buf * kC2N + part * 128;
             float* out = a.out + ((static_cast<int64_t>(clip) * a.frames_out + t0) * a.n_state + n);
             const float* pos = a.pos != nullptr ? a.pos + (static_cast<int64_t>(t0) * a.n_state + n) : nullptr;
+            const int last = a.frames_out - 1 - t0;              // last frame of the clip, relative to this warp's first
+            // a piece's 32 rows of the positional embedding: independent loads, asked for one piece ahead (the first
+            // piece's before the wait for the accumulator), so their latency is never on the epilogue's chain
+            float p[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p[i] = 0.f;
+            auto load_pos = [&](int piece) {
+                if (pos != nullptr && piece * 32 <= last) {
+                    const float* q = pos + static_cast<int64_t>(piece * 32) * a.n_state;
+                    if (piece * 32 + 31 <= last) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) p[i] = __ldg(q + static_cast<int64_t>(i) * a.n_state);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) p[i] = __ldg(q + static_cast<int64_t>(min(i, last - piece * 32)) * a.n_state);
+                    }
+                }
+            };
+            load_pos(0);
             mbar_wait(&bars.d_full[buf], (parities >> buf) & 1u, 100);
             parities ^= 1u << buf;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int last = a.frames_out - 1 - t0;              // last frame of the clip, relative to this warp's first
 #pragma unroll 1
             for (int piece = 0; piece < 4; ++piece) {
                 if (piece * 32 > last) {                         // (warp-uniform) nothing left of the clip: only the hand-over
@@ -231,14 +249,6 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
                         if (lane == 0) mbar_arrive(&bars.d_empty[buf]);
                     }
                     continue;
-                }
-                // the positional embedding's 32 rows first: independent loads, in flight during the accumulator's
-                float p[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) p[i] = 0.f;
-                if (pos != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) p[i] = __ldg(pos + static_cast<int64_t>(min(piece * 32 + i, last)) * a.n_state);
                 }
                 float d[32];
                 tmem_ld32(d_addr + piece * 32, d);
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
                     d[i] = g.x + p[i];
                     d[i + 1] = g.y + p[i + 1];
                 }
+                if (piece < 3) load_pos(piece + 1);
                 float* o = out + static_cast<int64_t>(piece * 32) * a.n_state;
                 if (piece * 32 + 31 <= last) {
 #pragma unroll

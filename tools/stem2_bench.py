@@ -42,8 +42,13 @@ def main():
         _native.check(lib.b200mel_stem_conv2_gelu_device(h1.data_ptr(), clips, 3000, packed.data_ptr(), b2.data_ptr(), pos.data_ptr(),
                                                          n_state, out.data_ptr(), s))
 
+    def conv2_plain():
+        _native.check(lib.b200mel_stem_conv2_gelu_device(h1.data_ptr(), clips, 3000, packed.data_ptr(), b2.data_ptr(), None,
+                                                         n_state, out.data_ptr(), s))
+
     t1 = timed(conv1, reps)
     t2 = timed(conv2, reps)
+    t2_plain = timed(conv2_plain, reps)
     t_stem = timed(lambda: b200.encoder_stem2(mel, w1, b1, packed, b2, pos), reps)
     t_all = timed(lambda: b200.log_mel_encoder_stem2(wave, w1, b1, packed, b2, pos), reps)
     flops2 = 2.0 * clips * 1500 * n_state * n_state * 3
@@ -52,6 +57,7 @@ def main():
     print(f"clips {clips} n_state {n_state}")
     print(f"conv1 + GELU -> half [B, 3000, {n_state}]   {t1:8.4f} ms  {bytes1 / t1 / 1e6:8.1f} GB/s")
     print(f"conv2 + GELU + pos -> [B, 1500, {n_state}]  {t2:8.4f} ms  {flops2 / t2 / 1e9:8.1f} TFLOP/s (f16 MMA)  {bytes2 / t2 / 1e6:8.1f} GB/s")
+    print(f"conv2 + GELU without pos                  {t2_plain:8.4f} ms")
     print(f"encoder_stem2 (mel in)              {t_stem:8.4f} ms")
     print(f"log_mel_encoder_stem2 (waveform in) {t_all:8.4f} ms  = {clips * 30 / 3600 / (t_all * 1e-3):8.1f} audio-hours/s")
 
