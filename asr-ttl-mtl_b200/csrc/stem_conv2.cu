@@ -14,16 +14,17 @@
 // the zero padding in front of the clip is the copy's out-of-bounds fill.  The weights come as half [3, n_state, n_state]
 // (tap, out channel, in channel: packed once by the host mirror), also one tensor copy per stage.
 //
-// One persistent CTA per SM, 10 warps: 8 epilogue (thread = channel; two warps per tensor-memory lane quadrant, 128 frames
+// One persistent CTA per SM, 18 warps: 16 epilogue (thread = channel; four warps per tensor-memory lane quadrant, 64 frames
 // each: bias, GELU, positional embedding, 128-byte row stores - a frame's 32 channels are one line), 1 MMA issue, 1 TMA
-// producer.  Four stages of 48 KB (A 128 x 64, B 256 x 64, 128-byte swizzle), two accumulators of 256 columns: the
-// epilogue of a tile overlaps the MMAs of the next.  CTAs with the other 128-channel slices walk the same tiles at the same
+// producer.  Operands in two rings (128-byte swizzle; see kC2AStages), two accumulators of 256 columns: the epilogue of a
+// tile overlaps the MMAs of the next.  CTAs with the other 128-channel slices walk the same tiles at the same
 // time, so h comes from HBM once.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -35,10 +36,19 @@ namespace {
 constexpr int kC2M = 128;                        // out channels per CTA = MMA M = TMEM lanes
 constexpr int kC2N = 256;                        // output frames per tile = MMA N
 constexpr int kC2K = 64;                         // in channels per stage: 128 bytes of half = one swizzle row
-constexpr int kC2Stages = 4;
-constexpr int kC2ABytes = kC2M * 128, kC2BBytes = kC2N * 128, kC2StageBytes = kC2ABytes + kC2BBytes;   // 16 + 32 KB
-constexpr int kC2Smem = kC2Stages * kC2StageBytes + 1024;                                              // + slack to align the base
-constexpr int kC2EpiWarps = 8, kC2WarpMma = 8, kC2WarpTma = 9, kC2Threads = 10 * 32;
+// Two rings.  Weights: six slots of 16 KB, one (tap, 64-channel chunk) box each.  Input frames: three slots of 33 KB, in turn
+// the ODD frames of a chunk - rows t0 - 1 .. t0 + 262, read by tap 0 from row 0 and by tap 2 from row 1 (a descriptor that
+// starts one 128-byte row into the buffer: the swizzle is a function of the shared-memory address, so the rows the tensor
+// copy wrote are the rows the MMA reads) - and its EVEN frames, rows t0 .. t0 + 255, read by tap 1.  The odd frames come
+// from L2 once for both taps: 113 KB per chunk instead of 144 - L2 -> shared memory is what bounds this kernel.
+constexpr int kC2AStages = 6, kC2BStages = 3;
+constexpr int kC2ABytes = kC2M * 128, kC2BBytes = kC2N * 128;        // 16 KB, 32 KB
+constexpr int kC2ExtraRows = 8, kC2BSlotBytes = kC2BBytes + kC2ExtraRows * 128;   // 33 KB
+constexpr int kC2BOffset = kC2AStages * kC2ABytes;
+constexpr int kC2Smem = kC2BOffset + kC2BStages * kC2BSlotBytes + 1024;           // + slack to align the base
+static_assert(kC2BSlotBytes % 1024 == 0 && kC2BOffset % 1024 == 0, "128-byte swizzle: operands 1024-byte aligned");
+constexpr int kC2EpiWarps = 16, kC2WarpMma = 16, kC2WarpTma = 17, kC2Threads = 18 * 32;
+constexpr int kC2PartCols = kC2N / (kC2EpiWarps / 4), kC2Piece = 16;   // frames of the tile per epilogue warp (64), per pull (16)
 constexpr uint32_t kC2Idesc = (1u << 4) | (static_cast<uint32_t>(kC2N >> 3) << 17) | (static_cast<uint32_t>(kC2M >> 4) << 24);   // f16 x f16 -> f32, K-major
 static_assert(kC2Smem <= 227 * 1024, "shared memory layout");
 
@@ -60,8 +70,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
     }
 }
 // K-major operand with 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
-    return (uint64_t{2} << 61) | (uint64_t{1} << 46) | (uint64_t{1024 >> 4} << 32) | (uint64_t{1} << 16) | ((smem_addr & 0x3ffffu) >> 4);
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr, uint32_t base_offset = 0) {
+    return (uint64_t{2} << 61) | (static_cast<uint64_t>(base_offset) << 49) | (uint64_t{1} << 46) | (uint64_t{1024 >> 4} << 32) | (uint64_t{1} << 16) |
+           ((smem_addr & 0x3ffffu) >> 4);
 }
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, bool accumulate) {
     asm volatile("{\n.reg .pred Q;\nsetp.ne.u32 Q, %4, 0;\n"
@@ -71,18 +82,15 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t t, float* d) {
-    uint32_t r[32];
+__device__ __forceinline__ void tmem_ld16(uint32_t t, float* d) {
+    uint32_t r[16];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(t) : "memory");
 #pragma unroll
-    for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(r[i]);
 }
 
 // GELU(v) = v Phi(v) = h + |h| erf(|h| sqrt 2), h = v / 2: the degree-6 fit of stem_conv.cu (tools/fit_gelu.py,
@@ -106,7 +114,7 @@ __device__ __forceinline__ float2 gelu2_from_half(float2 h) {
     return __ffma2_rn(make_float2(-a.x, -a.y), e, __fadd2_rn(h, a));
 }
 
-struct C2Barriers { uint64_t full[kC2Stages], empty[kC2Stages], d_full[2], d_empty[2]; };
+struct C2Barriers { uint64_t a_full[kC2AStages], a_empty[kC2AStages], b_full[kC2BStages], b_empty[kC2BStages], d_full[2], d_empty[2]; };
 
 struct C2Args {
     const float* bias;     // [n_state]
@@ -114,10 +122,17 @@ struct C2Args {
     float* out;            // [batch, frames_out, n_state]
     int64_t batch;
     int frames_out, n_state;
+    int debug;             // measurement switches (switches build only, B200MEL_C2_FLAGS): 1 no GELU / stores, 2 no MMAs, 4 no input copies
 };
+#if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
+#define C2_DEBUG(bit) ((a.debug & (bit)) != 0)
+#else
+#define C2_DEBUG(bit) false
+#endif
 
 __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2Args a, const __grid_constant__ CUtensorMap w_map,
-                                                                        const __grid_constant__ CUtensorMap h_map) {
+                                                                        const __grid_constant__ CUtensorMap h_map,
+                                                                        const __grid_constant__ CUtensorMap h8_map) {
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* const smem_raw = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
     __shared__ __align__(8) C2Barriers bars;
@@ -137,9 +152,13 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        for (int i = 0; i < kC2Stages; ++i) {
-            mbar_init(&bars.full[i], 1);         // the producer's arrive.expect_tx
-            mbar_init(&bars.empty[i], 1);        // tcgen05.commit
+        for (int i = 0; i < kC2AStages; ++i) {
+            mbar_init(&bars.a_full[i], 1);       // the producer's arrive.expect_tx
+            mbar_init(&bars.a_empty[i], 1);      // tcgen05.commit
+        }
+        for (int i = 0; i < kC2BStages; ++i) {
+            mbar_init(&bars.b_full[i], 1);
+            mbar_init(&bars.b_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars.d_full[i], 1);       // tcgen05.commit
@@ -155,49 +174,85 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
     if (warp == kC2WarpTma) {
         // ===== producer: per stage the weights' box (tap, slice, 64 in channels) and the tap's 256 rows of h =====
         if (lane == 0) {
-            uint32_t parity = 1;                                 // empty: the first use of a stage passes
-            int stage = 0;
+            uint32_t a_parity = 1, b_parity = 1;                 // empty: the first use of a slot passes
+            int a_slot = 0, b_slot = 0;
             for (int k = 0; k < my_tiles; ++k) {
                 const int64_t tile = walker + static_cast<int64_t>(k) * walkers;
                 const int clip = static_cast<int>(tile / tiles_per_clip);
                 const int t0 = static_cast<int>(tile % tiles_per_clip) * kC2N;
                 for (int j = 0; j < k_chunks; ++j) {
-                    for (int tap = 0; tap < 3; ++tap) {
-                        mbar_wait(&bars.empty[stage], parity, 32);
-                        unsigned char* sa = smem_raw + stage * kC2StageBytes;
-                        const uint32_t bar = smem_u32(&bars.full[stage]);
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kC2StageBytes) : "memory");
+                    auto weights = [&](int tap) {
+                        mbar_wait(&bars.a_empty[a_slot], a_parity, 32);
+                        const uint32_t bar = smem_u32(&bars.a_full[a_slot]);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kC2ABytes) : "memory");
                         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                                     ::"r"(smem_u32(sa)), "l"(&w_map), "r"(j * kC2K), "r"(slice * kC2M), "r"(tap), "r"(bar) : "memory");
-                        // input frame 2 t + tap - 1 = (row t - 1, odd), (row t, even), (row t, odd); row -1 is filled with zeros
+                                     ::"r"(smem_u32(smem_raw + a_slot * kC2ABytes)), "l"(&w_map), "r"(j * kC2K), "r"(slice * kC2M), "r"(tap), "r"(bar) : "memory");
+                        if (++a_slot == kC2AStages) { a_slot = 0; a_parity ^= 1u; }
+                    };
+                    // input frame 2 t + tap - 1 = (row t - 1, odd), (row t, even), (row t, odd); rows outside the clip are filled with zeros
+                    auto frames = [&](int odd) {
+                        mbar_wait(&bars.b_empty[b_slot], b_parity, 32);
+                        unsigned char* dst = smem_raw + kC2BOffset + b_slot * kC2BSlotBytes;
+                        const uint32_t bar = smem_u32(&bars.b_full[b_slot]);
+                        if (C2_DEBUG(4)) {
+                            mbar_arrive(&bars.b_full[b_slot]);
+                            if (++b_slot == kC2BStages) { b_slot = 0; b_parity ^= 1u; }
+                            return;
+                        }
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(odd ? kC2BSlotBytes : kC2BBytes) : "memory");
                         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                                     ::"r"(smem_u32(sa + kC2ABytes)), "l"(&h_map), "r"(j * kC2K), "r"(tap == 1 ? 0 : 1), "r"(tap == 0 ? t0 - 1 : t0),
-                                       "r"(clip), "r"(bar) : "memory");
-                        if (++stage == kC2Stages) { stage = 0; parity ^= 1u; }
-                    }
+                                     ::"r"(smem_u32(dst)), "l"(&h_map), "r"(j * kC2K), "r"(odd), "r"(t0 - odd), "r"(clip), "r"(bar) : "memory");
+                        if (odd)                                     // the rows behind the 256th: tap 2 reads one row further
+                            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                                         ::"r"(smem_u32(dst + kC2BBytes)), "l"(&h8_map), "r"(j * kC2K), "r"(1), "r"(t0 - 1 + kC2N), "r"(clip), "r"(bar) : "memory");
+                        if (++b_slot == kC2BStages) { b_slot = 0; b_parity ^= 1u; }
+                    };
+                    frames(1);
+                    weights(0);
+                    weights(2);
+                    frames(0);
+                    weights(1);
                 }
             }
         }
     } else if (warp == kC2WarpMma) {
         // ===== MMA issue: 4 MMAs of K 16 per stage =====
         if (lane == 0) {
-            uint32_t full_parity = 0, d_parity = 1;              // d_empty: the first two waits pass
-            int stage = 0, buf = 0;
+            uint32_t a_parity = 0, b_parity = 0, d_parity = 1;   // d_empty: the first two waits pass
+            int a_slot = 0, b_slot = 0, buf = 0;
             const uint32_t base = smem_u32(smem_raw);
             for (int k = 0; k < my_tiles; ++k) {
                 mbar_wait(&bars.d_empty[buf], d_parity, 32);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem + buf * kC2N;
-                for (int s = 0; s < 3 * k_chunks; ++s) {
-                    mbar_wait(&bars.full[stage], full_parity, 0);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t a_desc = sw128_desc(base + stage * kC2StageBytes);
-                    const uint64_t b_desc = sw128_desc(base + stage * kC2StageBytes + kC2ABytes);
+                for (int j = 0; j < k_chunks; ++j) {
+                    // one tap: wait for its weights, 4 MMAs of K 16 (32 bytes further inside the 128-byte row each), release the weights
+                    auto tap = [&](uint64_t b_desc, bool first) {
+                        mbar_wait(&bars.a_full[a_slot], a_parity, 0);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t a_desc = sw128_desc(base + a_slot * kC2ABytes);
 #pragma unroll
-                    for (int i = 0; i < kC2K / 16; ++i)          // K 16 = 32 bytes further inside the 128-byte row
-                        mma_f16_ss(d_tmem, a_desc + 2 * i, b_desc + 2 * i, s + i > 0);
-                    mma_commit(&bars.empty[stage]);
-                    if (++stage == kC2Stages) { stage = 0; full_parity ^= 1u; }
+                        for (int i = 0; i < kC2K / 16; ++i)
+                            if (!C2_DEBUG(2)) mma_f16_ss(d_tmem, a_desc + 2 * i, b_desc + 2 * i, !(first && i == 0));
+                        mma_commit(&bars.a_empty[a_slot]);
+                        if (++a_slot == kC2AStages) { a_slot = 0; a_parity ^= 1u; }
+                    };
+                    auto frames_ready = [&]() {
+                        mbar_wait(&bars.b_full[b_slot], b_parity, 0);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        return base + kC2BOffset + b_slot * kC2BSlotBytes;
+                    };
+                    auto frames_done = [&]() {
+                        mma_commit(&bars.b_empty[b_slot]);
+                        if (++b_slot == kC2BStages) { b_slot = 0; b_parity ^= 1u; }
+                    };
+                    const uint32_t odd = frames_ready();
+                    tap(sw128_desc(odd), j == 0);                                      // tap 0: rows t - 1
+                    tap(sw128_desc(odd + 128), false);                            // tap 2: rows t, the same buffer one row in
+                    frames_done();
+                    const uint32_t even = frames_ready();
+                    tap(sw128_desc(even), false);                                      // tap 1
+                    frames_done();
                 }
                 mma_commit(&bars.d_full[buf]);
                 buf ^= 1;
@@ -205,34 +260,37 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
             }
         }
     } else {
-        // ===== epilogue: thread = channel; warp w takes lane quadrant w % 4 and frames 128 (w / 4) .. + 127 of the tile =====
+        // ===== epilogue: thread = channel; warp w takes lane quadrant w % 4 and frames 64 (w / 4) .. + 63 of the tile, in pieces
+        // of 16.  Four warps per scheduler: the GELU is a chain of dependent packed FMAs, two warps left 60 % of the issue slots idle
+        // and the epilogue, not the tensor cores, set the pace. =====
         const int quadrant = warp & 3, part = warp >> 2;
         const int n = slice * kC2M + quadrant * 32 + lane;
         const float half_bias = 0.5f * __ldg(a.bias + n);
+        constexpr int kPieces = kC2PartCols / kC2Piece;
         uint32_t parities = 0;                                   // bit b: the parity of d_full[b] to wait for
         for (int k = 0; k < my_tiles; ++k) {
             const int buf = k & 1;
             const int64_t tile = walker + static_cast<int64_t>(k) * walkers;
             const int clip = static_cast<int>(tile / tiles_per_clip);
-            const int t0 = static_cast<int>(tile % tiles_per_clip) * kC2N + part * 128;
-            const uint32_t d_addr = tmem + (static_cast<uint32_t>(quadrant * 32) << 16) + buf * kC2N + part * 128;
+            const int t0 = static_cast<int>(tile % tiles_per_clip) * kC2N + part * kC2PartCols;
+            const uint32_t d_addr = tmem + (static_cast<uint32_t>(quadrant * 32) << 16) + buf * kC2N + part * kC2PartCols;
             float* out = a.out + ((static_cast<int64_t>(clip) * a.frames_out + t0) * a.n_state + n);
             const float* pos = a.pos != nullptr ? a.pos + (static_cast<int64_t>(t0) * a.n_state + n) : nullptr;
             const int last = a.frames_out - 1 - t0;              // last frame of the clip, relative to this warp's first
-            // a piece's 32 rows of the positional embedding: independent loads, asked for one piece ahead (the first
+            // a piece's 16 rows of the positional embedding: independent loads, asked for one piece ahead (the first
             // piece's before the wait for the accumulator), so their latency is never on the epilogue's chain
-            float p[32];
+            float p[kC2Piece];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) p[i] = 0.f;
+            for (int i = 0; i < kC2Piece; ++i) p[i] = 0.f;
             auto load_pos = [&](int piece) {
-                if (pos != nullptr && piece * 32 <= last) {
-                    const float* q = pos + static_cast<int64_t>(piece * 32) * a.n_state;
-                    if (piece * 32 + 31 <= last) {
+                if (pos != nullptr && piece * kC2Piece <= last) {
+                    const float* q = pos + static_cast<int64_t>(piece * kC2Piece) * a.n_state;
+                    if (piece * kC2Piece + kC2Piece - 1 <= last) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) p[i] = __ldg(q + static_cast<int64_t>(i) * a.n_state);
+                        for (int i = 0; i < kC2Piece; ++i) p[i] = __ldg(q + static_cast<int64_t>(i) * a.n_state);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) p[i] = __ldg(q + static_cast<int64_t>(min(i, last - piece * 32)) * a.n_state);
+                        for (int i = 0; i < kC2Piece; ++i) p[i] = __ldg(q + static_cast<int64_t>(min(i, last - piece * kC2Piece)) * a.n_state);
                     }
                 }
             };
@@ -241,39 +299,40 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
             parities ^= 1u << buf;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int piece = 0; piece < 4; ++piece) {
-                if (piece * 32 > last) {                         // (warp-uniform) nothing left of the clip: only the hand-over
-                    if (piece == 3) {
+            for (int piece = 0; piece < kPieces; ++piece) {
+                if (piece * kC2Piece > last) {                   // (warp-uniform) nothing left of the clip: only the hand-over
+                    if (piece == kPieces - 1) {
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars.d_empty[buf]);
                     }
                     continue;
                 }
-                float d[32];
-                tmem_ld32(d_addr + piece * 32, d);
+                float d[kC2Piece];
+                tmem_ld16(d_addr + piece * kC2Piece, d);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (piece == 3) {
+                if (piece == kPieces - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.d_empty[buf]);   // the warp's part of the accumulator is in registers
                 }
+                if (C2_DEBUG(1)) continue;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
+                for (int i = 0; i < kC2Piece; i += 2) {
                     const float2 h = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(0.5f, 0.5f), make_float2(half_bias, half_bias));
                     const float2 g = gelu2_from_half(h);
                     d[i] = g.x + p[i];
                     d[i + 1] = g.y + p[i + 1];
                 }
-                if (piece < 3) load_pos(piece + 1);
-                float* o = out + static_cast<int64_t>(piece * 32) * a.n_state;
-                if (piece * 32 + 31 <= last) {
+                if (piece + 1 < kPieces) load_pos(piece + 1);
+                float* o = out + static_cast<int64_t>(piece * kC2Piece) * a.n_state;
+                if (piece * kC2Piece + kC2Piece - 1 <= last) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[static_cast<int64_t>(i) * a.n_state] = d[i];
+                    for (int i = 0; i < kC2Piece; ++i) o[static_cast<int64_t>(i) * a.n_state] = d[i];
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (piece * 32 + i <= last) o[static_cast<int64_t>(i) * a.n_state] = d[i];
+                    for (int i = 0; i < kC2Piece; ++i)
+                        if (piece * kC2Piece + i <= last) o[static_cast<int64_t>(i) * a.n_state] = d[i];
                 }
             }
         }
@@ -317,9 +376,10 @@ cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames
     const EncodeFn encode = tensor_map_encoder();
     if (encode == nullptr) return cudaErrorNotSupported;
     const uint64_t c = static_cast<uint64_t>(n_state);
-    CUtensorMap w_map, h_map;
+    CUtensorMap w_map, h_map, h8_map;
     std::memset(&w_map, 0, sizeof(w_map));
     std::memset(&h_map, 0, sizeof(h_map));
+    std::memset(&h8_map, 0, sizeof(h8_map));
     {   // weights: half [3 taps][n_state out][n_state in]; box = 64 in channels x 128 out channels of one tap
         const cuuint64_t dims[3] = {c, c, 3};
         const cuuint64_t strides[2] = {c * 2, c * c * 2};
@@ -337,6 +397,10 @@ cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames
         if (encode(&h_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(h_fm16), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
+        const cuuint32_t box8[4] = {kC2K, 1, kC2ExtraRows, 1};   // the odd frames behind the 256th row
+        if (encode(&h8_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(h_fm16), dims, strides, box8, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
     }
     const int sms = sms_by_device[device];
     const int slices = n_state / kC2M;
@@ -344,9 +408,12 @@ cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames
     int64_t walkers = sms / slices;                                   // CTAs per slice; every CTA of the grid is resident
     if (walkers < 1) walkers = 1;
     if (walkers > tiles) walkers = tiles;
-    const C2Args a{bias, pos, out, batch, frames_out, n_state};
+    C2Args a{bias, pos, out, batch, frames_out, n_state, 0};
+#if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
+    if (std::getenv("B200MEL_C2_FLAGS") != nullptr) a.debug = std::atoi(std::getenv("B200MEL_C2_FLAGS"));
+#endif
     ProfileScope profile(3, stream);
-    stem_conv2_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kC2Threads, kC2Smem, stream>>>(a, w_map, h_map);
+    stem_conv2_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kC2Threads, kC2Smem, stream>>>(a, w_map, h_map, h8_map);
     count_launch();
     return cudaGetLastError();
 }

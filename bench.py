@@ -587,6 +587,41 @@ def run_own_arm(args) -> None:
             "host_in_host_out_ms_median_of_30": 1e3 * statistics.median(laps),
             "device_in_device_out_ms_median_of_30": 1e3 * statistics.median(dev_laps),
             "value": CLIP_SECONDS / 3600.0 / statistics.median(laps), "unit": "audio-hours/s"}
+        if n_mels == 80:
+            # the step behind the path: the encoder stem of model.py:193-197 on the same 256 clips, n_state 384
+            # (Whisper tiny's) - conv1 + GELU, conv2 (stride 2) + GELU, permute, positional embedding; torch's cudnn pair beside it
+            import torch.nn.functional as F
+
+            n_state = 384
+            gs = torch.Generator(device=device).manual_seed(77)
+            w1 = (torch.rand(n_state, 80, 3, generator=gs, device=device) * 2 - 1) / 240 ** 0.5
+            b1 = (torch.rand(n_state, generator=gs, device=device) * 2 - 1) / 240 ** 0.5
+            w2 = (torch.rand(n_state, n_state, 3, generator=gs, device=device) * 2 - 1) / (3 * n_state) ** 0.5
+            b2 = (torch.rand(n_state, generator=gs, device=device) * 2 - 1) / (3 * n_state) ** 0.5
+            pos = torch.rand(N_FRAMES // 2, n_state, generator=gs, device=device)
+            packed = b200.pack_conv2_weight(w2)
+            mel_s = b200.log_mel_spectrogram_batch(inputs[0], n_mels=80)
+
+            def torch_stem(i: int):
+                y = F.gelu(F.conv1d(mel_s, w1, b1, padding=1))
+                return F.gelu(F.conv1d(y, w2, b2, stride=2, padding=1)).permute(0, 2, 1) + pos
+
+            stem_steps = max(3, min(args.steps, 20))
+            rows_s = {}
+            for name, fn in (("encoder_stem2_ms", lambda i: b200.encoder_stem2(mel_s, w1, b1, packed, b2, pos)),
+                             ("log_mel_encoder_stem2_ms", lambda i: b200.log_mel_encoder_stem2(inputs[i & 1], w1, b1, packed, b2, pos)),
+                             ("torch_cudnn_tf32_stem_ms", torch_stem)):
+                for i in range(3):
+                    fn(i)
+                ms_s, _ = timed_steps(fn, stem_steps, local_rank)
+                rows_s[name] = ms_s / stem_steps
+            configs["stem"] = {
+                "workload": f"encoder stem (model.py:193-197) behind the front-end, {B} clips, n_state {n_state}: mel [B, 80, 3000] -> float32 [B, 1500, {n_state}]",
+                **rows_s, "conv2_gflop": 2.0 * B * (N_FRAMES // 2) * n_state * n_state * 3 / 1e9,
+                "waveform_to_stem_audio_hours_per_s": B * CLIP_SECONDS / 3600.0 / (rows_s["log_mel_encoder_stem2_ms"] / 1e3),
+                "arithmetic": "conv1 TF32 operands, conv2 IEEE-half operands (TF32's significand), float32 accumulation in tensor memory"}
+            del mel_s, packed, pos
+            torch.cuda.empty_cache()
         extra["configs"] = configs
 
         # ---- sustained: >= 2 s of back-to-back steps, clocks sampled while they run (last: it leaves the GPU at its power cap) ----
