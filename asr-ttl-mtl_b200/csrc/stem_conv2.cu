@@ -15,7 +15,7 @@
 // (tap, out channel, in channel: packed once by the host mirror), also one tensor copy per stage.
 //
 // One persistent CTA per SM, 18 warps: 16 epilogue (thread = channel; four warps per tensor-memory lane quadrant, 64 frames
-// each: bias, GELU, positional embedding, 128-byte row stores - a frame's 32 channels are one line), 1 MMA issue, 1 TMA
+// each: bias, GELU, positional embedding, staged pieces out by TMA tensor store - a frame's 32 channels are one line), 1 MMA issue, 1 TMA
 // producer.  Operands in two rings (128-byte swizzle; see kC2AStages), two accumulators of 256 columns: the epilogue of a
 // tile overlaps the MMAs of the next.  CTAs with the other 128-channel slices walk the same tiles at the same
 // time, so h comes from HBM once.
@@ -36,16 +36,18 @@ namespace {
 constexpr int kC2M = 128;                        // out channels per CTA = MMA M = TMEM lanes
 constexpr int kC2N = 256;                        // output frames per tile = MMA N
 constexpr int kC2K = 64;                         // in channels per stage: 128 bytes of half = one swizzle row
-// Two rings.  Weights: six slots of 16 KB, one (tap, 64-channel chunk) box each.  Input frames: three slots of 33 KB, in turn
+// Two rings.  Weights: five slots of 16 KB, one (tap, 64-channel chunk) box each.  Input frames: three slots of 33 KB, in turn
 // the ODD frames of a chunk - rows t0 - 1 .. t0 + 262, read by tap 0 from row 0 and by tap 2 from row 1 (a descriptor that
 // starts one 128-byte row into the buffer: the swizzle is a function of the shared-memory address, so the rows the tensor
 // copy wrote are the rows the MMA reads) - and its EVEN frames, rows t0 .. t0 + 255, read by tap 1.  The odd frames come
 // from L2 once for both taps: 113 KB per chunk instead of 144 - L2 -> shared memory is what bounds this kernel.
-constexpr int kC2AStages = 6, kC2BStages = 3;
+constexpr int kC2AStages = 5, kC2BStages = 3;
 constexpr int kC2ABytes = kC2M * 128, kC2BBytes = kC2N * 128;        // 16 KB, 32 KB
 constexpr int kC2ExtraRows = 8, kC2BSlotBytes = kC2BBytes + kC2ExtraRows * 128;   // 33 KB
 constexpr int kC2BOffset = kC2AStages * kC2ABytes;
-constexpr int kC2Smem = kC2BOffset + kC2BStages * kC2BSlotBytes + 1024;           // + slack to align the base
+constexpr int kC2OutOffset = kC2BOffset + kC2BStages * kC2BSlotBytes;             // the epilogue warps' staging pieces: [16 frames][32 channels] float
+constexpr int kC2OutPieceBytes = 16 * 128;
+constexpr int kC2Smem = kC2OutOffset + 16 * kC2OutPieceBytes + 1024;              // + slack to align the base
 static_assert(kC2BSlotBytes % 1024 == 0 && kC2BOffset % 1024 == 0, "128-byte swizzle: operands 1024-byte aligned");
 constexpr int kC2EpiWarps = 16, kC2WarpMma = 16, kC2WarpTma = 17, kC2Threads = 18 * 32;
 constexpr int kC2PartCols = kC2N / (kC2EpiWarps / 4), kC2Piece = 16;   // frames of the tile per epilogue warp (64), per pull (16)
@@ -122,6 +124,7 @@ struct C2Args {
     float* out;            // [batch, frames_out, n_state]
     int64_t batch;
     int frames_out, n_state;
+    int out_tma;           // out_map describes `out` as [batch * frames_out rows, n_state]: whole pieces leave by TMA tensor store
     int debug;             // measurement switches (switches build only, B200MEL_C2_FLAGS): 1 no GELU / stores, 2 no MMAs, 4 no input copies
 };
 #if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
@@ -132,7 +135,8 @@ struct C2Args {
 
 __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2Args a, const __grid_constant__ CUtensorMap w_map,
                                                                         const __grid_constant__ CUtensorMap h_map,
-                                                                        const __grid_constant__ CUtensorMap h8_map) {
+                                                                        const __grid_constant__ CUtensorMap h8_map,
+                                                                        const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* const smem_raw = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
     __shared__ __align__(8) C2Barriers bars;
@@ -267,6 +271,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
         const int n = slice * kC2M + quadrant * 32 + lane;
         const float half_bias = 0.5f * __ldg(a.bias + n);
         constexpr int kPieces = kC2PartCols / kC2Piece;
+        const uint32_t staging = smem_u32(smem_raw + kC2OutOffset + warp * kC2OutPieceBytes);
         uint32_t parities = 0;                                   // bit b: the parity of d_full[b] to wait for
         for (int k = 0; k < my_tiles; ++k) {
             const int buf = k & 1;
@@ -326,7 +331,21 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
                 }
                 if (piece + 1 < kPieces) load_pos(piece + 1);
                 float* o = out + static_cast<int64_t>(piece * kC2Piece) * a.n_state;
-                if (piece * kC2Piece + kC2Piece - 1 <= last) {
+                if (piece * kC2Piece + kC2Piece - 1 <= last && a.out_tma) {
+                    // a whole piece inside the clip: staged as [16 frames][32 channels] (a row = one 128-byte line of the result) and
+                    // out with one TMA tensor store - no L1 tag traffic, one instruction instead of sixteen stores
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous piece has been read
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < kC2Piece; ++i) asm volatile("st.shared.f32 [%0], %1;" ::"r"(staging + i * 128 + lane * 4), "f"(d[i]) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&out_map), "r"(slice * kC2M + quadrant * 32), "r"(clip * a.frames_out + t0 + piece * kC2Piece), "r"(staging) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else if (piece * kC2Piece + kC2Piece - 1 <= last) {
 #pragma unroll
                     for (int i = 0; i < kC2Piece; ++i) o[static_cast<int64_t>(i) * a.n_state] = d[i];
                 } else {
@@ -337,6 +356,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
             }
         }
     }
+    if (warp < kC2EpiWarps && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staging pieces live until the stores have read them
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -376,7 +396,9 @@ cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames
     const EncodeFn encode = tensor_map_encoder();
     if (encode == nullptr) return cudaErrorNotSupported;
     const uint64_t c = static_cast<uint64_t>(n_state);
-    CUtensorMap w_map, h_map, h8_map;
+    CUtensorMap w_map, h_map, h8_map, out_map;
+    std::memset(&out_map, 0, sizeof(out_map));
+    int out_tma = 0;
     std::memset(&w_map, 0, sizeof(w_map));
     std::memset(&h_map, 0, sizeof(h_map));
     std::memset(&h8_map, 0, sizeof(h8_map));
@@ -402,18 +424,28 @@ cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
+    if (reinterpret_cast<uintptr_t>(out) % 16 == 0 && batch * frames_out < (int64_t{1} << 31)) {
+        // the result as the TMA unit sees it: [batch * frames_out rows, n_state] float, boxes of 16 frames x 32 channels
+        const cuuint64_t dims[2] = {c, static_cast<cuuint64_t>(batch * frames_out)};
+        const cuuint64_t strides[1] = {c * 4};
+        const cuuint32_t box[2] = {32, kC2Piece};
+        const cuuint32_t elem[2] = {1, 1};
+        if (encode(&out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            out_tma = 1;
+    }
     const int sms = sms_by_device[device];
     const int slices = n_state / kC2M;
     const int64_t tiles = batch * ((frames_out + kC2N - 1) / kC2N);
     int64_t walkers = sms / slices;                                   // CTAs per slice; every CTA of the grid is resident
     if (walkers < 1) walkers = 1;
     if (walkers > tiles) walkers = tiles;
-    C2Args a{bias, pos, out, batch, frames_out, n_state, 0};
+    C2Args a{bias, pos, out, batch, frames_out, n_state, out_tma, 0};
 #if defined(B200MEL_TC_TRACE) || defined(B200MEL_TC_SWITCHES)
     if (std::getenv("B200MEL_C2_FLAGS") != nullptr) a.debug = std::atoi(std::getenv("B200MEL_C2_FLAGS"));
 #endif
     ProfileScope profile(3, stream);
-    stem_conv2_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kC2Threads, kC2Smem, stream>>>(a, w_map, h_map, h8_map);
+    stem_conv2_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kC2Threads, kC2Smem, stream>>>(a, w_map, h_map, h8_map, out_map);
     count_launch();
     return cudaGetLastError();
 }
