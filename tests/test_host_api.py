@@ -89,6 +89,31 @@ def test_no_cpu_fallback():
         audio.log_mel_spectrogram(np.zeros(16000, np.float32))
 
 
+def test_pack_conv2_weight_is_tap_major_half():
+    """The second stem layer's operand (model.py:180): conv2.weight [n, c, 3] -> half [3, n, c]."""
+    w = torch.arange(4 * 4 * 3, dtype=torch.float32).reshape(4, 4, 3) / 7
+    packed = b200.pack_conv2_weight(w)
+    assert packed.dtype == torch.float16 and tuple(packed.shape) == (3, 4, 4) and packed.is_contiguous()
+    for k in range(3):
+        assert torch.equal(packed[k], w[:, :, k].half())
+    with pytest.raises(ValueError):
+        b200.pack_conv2_weight(torch.zeros(4, 5, 3))
+    with pytest.raises(ValueError):
+        b200.pack_conv2_weight(torch.zeros(4, 4, 5))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_encoder_stem_has_no_cpu_fallback():
+    w1, b1 = torch.zeros(384, 80, 3), torch.zeros(384)
+    w2, b2 = torch.zeros(384, 384, 3), torch.zeros(384)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200.encoder_stem(torch.zeros(1, 80, 100), w1, b1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200.encoder_stem2(torch.zeros(1, 80, 100), w1, b1, w2, b2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200.log_mel_encoder_stem2(torch.zeros(1, 16000), w1, b1, w2, b2)
+
+
 def test_install_rebinds_consumer_namespaces():
     fake_audio = types.ModuleType("whisper.audio")
     fake_pkg = types.ModuleType("whisper")
