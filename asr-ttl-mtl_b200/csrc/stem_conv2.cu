@@ -40,7 +40,7 @@ constexpr int kC2K = 64;                         // in channels per stage: 128 b
 // the ODD frames of a chunk - rows t0 - 1 .. t0 + 262, read by tap 0 from row 0 and by tap 2 from row 1 (a descriptor that
 // starts one 128-byte row into the buffer: the swizzle is a function of the shared-memory address, so the rows the tensor
 // copy wrote are the rows the MMA reads) - and its EVEN frames, rows t0 .. t0 + 255, read by tap 1.  The odd frames come
-// from L2 once for both taps: 113 KB per chunk instead of 144 - L2 -> shared memory is what bounds this kernel.
+// from L2 once for both taps: 113 KB per chunk instead of 144 through L2 and into shared memory.
 constexpr int kC2AStages = 5, kC2BStages = 3;
 constexpr int kC2ABytes = kC2M * 128, kC2BBytes = kC2N * 128;        // 16 KB, 32 KB
 constexpr int kC2ExtraRows = 8, kC2BSlotBytes = kC2BBytes + kC2ExtraRows * 128;   // 33 KB
