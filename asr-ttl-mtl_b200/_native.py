@@ -43,7 +43,7 @@ SYMBOLS = {
                                                c_void_p, c_void_p]),
     "b200mel_stem_conv1_gelu_fm16_device": (c_int, [c_void_p, c_void_p, c_uint, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int,
                                                     c_void_p, c_void_p]),
-    "b200mel_stem_conv2_gelu_device": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200mel_stem_conv2_gelu_device": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_uint, c_void_p]),
     "b200mel_mel_windows_device": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint, c_void_p]),
     "b200mel_logmel_host": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                     c_void_p, c_uint, c_int]),

@@ -336,14 +336,15 @@ int b200mel_stem_conv1_gelu_fm16_device(const float* mel, const void* workspace,
 }
 
 int b200mel_stem_conv2_gelu_device(const void* h_fm16, int64_t batch, int64_t frames_padded, const void* weight_f16, const float* bias,
-                                   const float* positional_embedding, int n_state, float* out, void* stream) {
+                                   const float* positional_embedding, int n_state, void* out, unsigned flags, void* stream) {
+    if (flags & ~B200MEL_FLAG_OUT_F16) return B200MEL_ERR_BAD_ARGUMENT;
     if (h_fm16 == nullptr || weight_f16 == nullptr || bias == nullptr || out == nullptr) return B200MEL_ERR_NULL_POINTER;
     if (batch < 0 || frames_padded < 0 || frames_padded % 2 != 0 || frames_padded > 0x7ffffff0 || n_state <= 0 || n_state % 128 != 0 ||
         n_state > 128 * 148 || batch > 0x7fffffff)
         return B200MEL_ERR_BAD_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(h_fm16) | reinterpret_cast<uintptr_t>(weight_f16)) % 16 != 0) return B200MEL_ERR_BAD_ARGUMENT;
     B200_CUDA(launch_stem_conv2_gelu(h_fm16, batch, static_cast<int>(frames_padded), weight_f16, bias, positional_embedding, n_state, out,
-                                     static_cast<cudaStream_t>(stream)));
+                                     (flags & B200MEL_FLAG_OUT_F16) ? 1 : 0, static_cast<cudaStream_t>(stream)));
     return B200MEL_OK;
 }
 

@@ -61,9 +61,9 @@ cudaError_t launch_stem_conv1_gelu(const float* mel, const uint32_t* max_keys, c
 
 // Encoder stem, second layer (stem_conv2.cu): out[b, t, n] = gelu(conv1d(h, weight, bias, kernel 3, stride 2, padding 1))[b, n, t]
 // (+ pos[t, n]), t < frames_padded / 2.  h_fm16: half [batch, frames_padded (even), n_state] as launch_stem_conv1_gelu leaves
-// it; weight_f16: half [3, n_state, n_state] (tap, out, in); n_state % 128 == 0.
+// it; weight_f16: half [3, n_state, n_state] (tap, out, in); n_state % 128 == 0; out: float32, or IEEE half with out_f16.
 cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames_padded, const void* weight_f16, const float* bias, const float* pos,
-                                   int n_state, float* out, cudaStream_t stream);
+                                   int n_state, void* out, int out_f16, cudaStream_t stream);
 
 // Window cut behind the front-end (mel_windows.cu): out[w, m, j] = mel[m, seeks[w] + j] for j < sizes[w] (nullptr: the whole
 // window), zeros behind - transcribe.py:282-286 for n_windows windows at once, float32 or half.

@@ -121,7 +121,7 @@ struct C2Barriers { uint64_t a_full[kC2AStages], a_empty[kC2AStages], b_full[kC2
 struct C2Args {
     const float* bias;     // [n_state]
     const float* pos;      // [frames_out, n_state] or nullptr
-    float* out;            // [batch, frames_out, n_state]
+    void* out;             // [batch, frames_out, n_state], float or half (the kernel's OutT)
     int64_t batch;
     int frames_out, n_state;
     int out_tma;           // out_map describes `out` as [batch * frames_out rows, n_state]: whole pieces leave by TMA tensor store
@@ -133,6 +133,11 @@ struct C2Args {
 #define C2_DEBUG(bit) false
 #endif
 
+template <typename OutT> __device__ __forceinline__ OutT c2_out(float v);
+template <> __device__ __forceinline__ float c2_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half c2_out<__half>(float v) { return __float2half_rn(v); }
+
+template <typename OutT>
 __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2Args a, const __grid_constant__ CUtensorMap w_map,
                                                                         const __grid_constant__ CUtensorMap h_map,
                                                                         const __grid_constant__ CUtensorMap h8_map,
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
             const int clip = static_cast<int>(tile / tiles_per_clip);
             const int t0 = static_cast<int>(tile % tiles_per_clip) * kC2N + part * kC2PartCols;
             const uint32_t d_addr = tmem + (static_cast<uint32_t>(quadrant * 32) << 16) + buf * kC2N + part * kC2PartCols;
-            float* out = a.out + ((static_cast<int64_t>(clip) * a.frames_out + t0) * a.n_state + n);
+            OutT* out = static_cast<OutT*>(a.out) + ((static_cast<int64_t>(clip) * a.frames_out + t0) * a.n_state + n);
             const float* pos = a.pos != nullptr ? a.pos + (static_cast<int64_t>(t0) * a.n_state + n) : nullptr;
             const int last = a.frames_out - 1 - t0;              // last frame of the clip, relative to this warp's first
             // a piece's 16 rows of the positional embedding: independent loads, asked for one piece ahead (the first
@@ -330,14 +335,19 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
                     d[i + 1] = g.y + p[i + 1];
                 }
                 if (piece + 1 < kPieces) load_pos(piece + 1);
-                float* o = out + static_cast<int64_t>(piece * kC2Piece) * a.n_state;
+                OutT* o = out + static_cast<int64_t>(piece * kC2Piece) * a.n_state;
                 if (piece * kC2Piece + kC2Piece - 1 <= last && a.out_tma) {
-                    // a whole piece inside the clip: staged as [16 frames][32 channels] (a row = one 128-byte line of the result) and
-                    // out with one TMA tensor store - no L1 tag traffic, one instruction instead of sixteen stores
+                    // a whole piece inside the clip: staged as [16 frames][32 channels] (a row = 128 / 64 contiguous bytes of the result)
+                    // and out with one TMA tensor store - no L1 tag traffic, one instruction instead of sixteen stores
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous piece has been read
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < kC2Piece; ++i) asm volatile("st.shared.f32 [%0], %1;" ::"r"(staging + i * 128 + lane * 4), "f"(d[i]) : "memory");
+                    for (int i = 0; i < kC2Piece; ++i) {
+                        if constexpr (sizeof(OutT) == 4)
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(staging + i * 128 + lane * 4), "f"(d[i]) : "memory");
+                        else
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(staging + i * 64 + lane * 2), "h"(__half_as_ushort(__float2half_rn(d[i]))) : "memory");
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
@@ -347,11 +357,11 @@ __global__ void __launch_bounds__(kC2Threads, 1) stem_conv2_gelu_kernel(const C2
                     }
                 } else if (piece * kC2Piece + kC2Piece - 1 <= last) {
 #pragma unroll
-                    for (int i = 0; i < kC2Piece; ++i) o[static_cast<int64_t>(i) * a.n_state] = d[i];
+                    for (int i = 0; i < kC2Piece; ++i) o[static_cast<int64_t>(i) * a.n_state] = c2_out<OutT>(d[i]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < kC2Piece; ++i)
-                        if (piece * kC2Piece + i <= last) o[static_cast<int64_t>(i) * a.n_state] = d[i];
+                        if (piece * kC2Piece + i <= last) o[static_cast<int64_t>(i) * a.n_state] = c2_out<OutT>(d[i]);
                 }
             }
         }
@@ -377,7 +387,7 @@ EncodeFn tensor_map_encoder() {
 }  // namespace
 
 cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames_padded, const void* weight_f16, const float* bias, const float* pos,
-                                   int n_state, float* out, cudaStream_t stream) {
+                                   int n_state, void* out, int out_f16, cudaStream_t stream) {
     const int frames_out = frames_padded / 2;
     if (batch <= 0 || frames_out <= 0) return cudaSuccess;
     constexpr int kMaxDevices = 64;
@@ -387,7 +397,8 @@ cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames
     if (err != cudaSuccess) return err;
     if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
     if (sms_by_device[device] == 0) {
-        err = cudaFuncSetAttribute(stem_conv2_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2Smem);
+        err = cudaFuncSetAttribute(stem_conv2_gelu_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2Smem);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(stem_conv2_gelu_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2Smem);
         int count = 0;
         if (err == cudaSuccess) err = cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device);
         if (err != cudaSuccess) return err;
@@ -425,12 +436,12 @@ cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames
             return cudaErrorInvalidValue;
     }
     if (reinterpret_cast<uintptr_t>(out) % 16 == 0 && batch * frames_out < (int64_t{1} << 31)) {
-        // the result as the TMA unit sees it: [batch * frames_out rows, n_state] float, boxes of 16 frames x 32 channels
+        // the result as the TMA unit sees it: [batch * frames_out rows, n_state] float / half, boxes of 16 frames x 32 channels
         const cuuint64_t dims[2] = {c, static_cast<cuuint64_t>(batch * frames_out)};
-        const cuuint64_t strides[1] = {c * 4};
+        const cuuint64_t strides[1] = {c * (out_f16 ? 2 : 4)};
         const cuuint32_t box[2] = {32, kC2Piece};
         const cuuint32_t elem[2] = {1, 1};
-        if (encode(&out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        if (encode(&out_map, out_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
             out_tma = 1;
     }
@@ -445,7 +456,8 @@ cudaError_t launch_stem_conv2_gelu(const void* h_fm16, int64_t batch, int frames
     if (std::getenv("B200MEL_C2_FLAGS") != nullptr) a.debug = std::atoi(std::getenv("B200MEL_C2_FLAGS"));
 #endif
     ProfileScope profile(3, stream);
-    stem_conv2_gelu_kernel<<<static_cast<unsigned>(walkers * slices), kC2Threads, kC2Smem, stream>>>(a, w_map, h_map, h8_map, out_map);
+    if (out_f16) stem_conv2_gelu_kernel<__half><<<static_cast<unsigned>(walkers * slices), kC2Threads, kC2Smem, stream>>>(a, w_map, h_map, h8_map, out_map);
+    else stem_conv2_gelu_kernel<float><<<static_cast<unsigned>(walkers * slices), kC2Threads, kC2Smem, stream>>>(a, w_map, h_map, h8_map, out_map);
     count_launch();
     return cudaGetLastError();
 }

@@ -134,11 +134,13 @@ def _check_conv2_params(weight, bias, pos, n_state, frames_out, device):
     return packed, bias, pos
 
 
-def _conv2(lib, h1, batch, frames_padded, packed, bias2, pos, n_state, stream):
-    out = torch.empty((batch, frames_padded // 2, n_state), dtype=torch.float32, device=h1.device)
+def _conv2(lib, h1, batch, frames_padded, packed, bias2, pos, n_state, stream, dtype=torch.float32):
+    if dtype not in (torch.float32, torch.float16):
+        raise ValueError(f"encoder stem: dtype must be torch.float32 or torch.float16, got {dtype}")
+    out = torch.empty((batch, frames_padded // 2, n_state), dtype=dtype, device=h1.device)
     _native.check(lib.b200mel_stem_conv2_gelu_device(
         h1.data_ptr(), batch, frames_padded, packed.data_ptr(), bias2.data_ptr(), None if pos is None else pos.data_ptr(),
-        n_state, out.data_ptr(), stream.cuda_stream))
+        n_state, out.data_ptr(), _native.FLAG_OUT_F16 if dtype == torch.float16 else 0, stream.cuda_stream))
     for t in (h1, packed, bias2) + (() if pos is None else (pos,)):
         t.record_stream(stream)
     return out
@@ -154,7 +156,8 @@ def _intermediate(batch, n_frames, n_state, device):
 
 
 def encoder_stem2(mel: torch.Tensor, conv1_weight: torch.Tensor, conv1_bias: torch.Tensor, conv2_weight: torch.Tensor,
-                  conv2_bias: torch.Tensor, positional_embedding: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  conv2_bias: torch.Tensor, positional_embedding: Optional[torch.Tensor] = None, *,
+                  dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """The stem of ``AudioEncoder.forward`` (model.py:193-197) for a CUDA float32 ``mel`` ``[B, 80, T]``::
 
         x = F.gelu(conv1(mel)); x = F.gelu(conv2(x)); x = x.permute(0, 2, 1); x = x + positional_embedding
@@ -162,7 +165,8 @@ def encoder_stem2(mel: torch.Tensor, conv1_weight: torch.Tensor, conv1_bias: tor
     -> float32 ``[B, (T + 1) // 2, n_state]`` in two launches.  conv1 as ``encoder_stem`` (TF32 operands); its result goes
     to conv2 as IEEE half ``[B, T, n_state]`` (frames major: the layout the second GEMM's operand copies want) and conv2
     multiplies half operands with float32 accumulation - the 11-bit significand of TF32, i.e. of torch's own convolution.
-    ``conv2_weight``: ``conv2.weight`` or ``pack_conv2_weight(conv2.weight)``; ``positional_embedding`` optional."""
+    ``conv2_weight``: ``conv2.weight`` or ``pack_conv2_weight(conv2.weight)``; ``positional_embedding`` optional;
+    ``dtype=torch.float16``: the float32 result rounded once, for a half-precision model (model.py:197 ``.to(x.dtype)``)."""
     _audio._require_cuda()
     if not mel.is_cuda or mel.dtype != torch.float32 or mel.dim() != 3:
         raise ValueError("encoder_stem2: mel must be a CUDA float32 [B, n_mels, T] tensor")
@@ -179,18 +183,19 @@ def encoder_stem2(mel: torch.Tensor, conv1_weight: torch.Tensor, conv1_bias: tor
             stream.cuda_stream))
         for t in (x, w1, b1):
             t.record_stream(stream)
-        return _conv2(lib, h1, batch, frames_padded, packed, b2, pos, n_state, stream)
+        return _conv2(lib, h1, batch, frames_padded, packed, b2, pos, n_state, stream, dtype)
 
 
 def log_mel_encoder_stem2(audio: torch.Tensor, conv1_weight: torch.Tensor, conv1_bias: torch.Tensor, conv2_weight: torch.Tensor,
                           conv2_bias: torch.Tensor, positional_embedding: Optional[torch.Tensor] = None, *, padding: int = 0,
-                          lengths=None, global_max: bool = False) -> torch.Tensor:
+                          lengths=None, global_max: bool = False, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """``encoder_stem2(log_mel_spectrogram_batch(audio, 80, padding, lengths=lengths), ...)`` for a CUDA ``[B, L]`` waveform
     (float32 or int16 PCM) in three launches: front-end (un-clamped output, ``B200MEL_FLAG_DEFER_CLAMP``), conv1 (clamps on
     load), conv2 - waveform in, the transformer blocks' input out (dataset.py:80-96 -> model.py:193-197)."""
     _audio._require_cuda()
     if not audio.is_cuda or audio.dim() != 2:
         raise ValueError("log_mel_encoder_stem2: audio must be a CUDA [B, L] tensor")
+    out_dtype = dtype
     dtype = _audio._validate_waveform(audio, True)
     wave = audio.detach()
     if wave.stride(-1) != 1 or (wave.shape[0] > 1 and wave.stride(0) < wave.shape[1]):
@@ -224,4 +229,4 @@ def log_mel_encoder_stem2(audio: torch.Tensor, conv1_weight: torch.Tensor, conv1
             n_state, h1.data_ptr(), stream.cuda_stream))
         for t in (wave, mel, workspace, w1, b1):
             t.record_stream(stream)
-        return _conv2(lib, h1, batch, frames_padded, packed, b2, pos, n_state, stream)
+        return _conv2(lib, h1, batch, frames_padded, packed, b2, pos, n_state, stream, out_dtype)

@@ -157,12 +157,14 @@ int b200mel_stem_conv1_gelu_device(const float* mel, const void* workspace, unsi
  *   bias       device float32 [n_state]
  *   positional_embedding  device float32 [frames_padded / 2, n_state] or NULL (model.py:197; the reference asserts
  *              frames_padded / 2 == n_ctx = 1500)
- *   out        device float32 [batch, frames_padded / 2, n_state] - the layout behind the permute of model.py:195 */
+ *   out        device float32 [batch, frames_padded / 2, n_state] - the layout behind the permute of model.py:195 - or, with
+ *              flags = B200MEL_FLAG_OUT_F16, IEEE half: the float32 result rounded once (what `.to(x.dtype)` of model.py:197
+ *              hands the blocks of a half-precision model, transcribe.py:127).  Other flags: B200MEL_ERR_BAD_ARGUMENT */
 int b200mel_stem_conv1_gelu_fm16_device(const float* mel, const void* workspace, unsigned flags, int64_t batch, int n_mels,
                                         int64_t n_frames, const float* weight, const float* bias, int n_state, void* out_fm16,
                                         void* stream);
 int b200mel_stem_conv2_gelu_device(const void* h_fm16, int64_t batch, int64_t frames_padded, const void* weight_f16, const float* bias,
-                                   const float* positional_embedding, int n_state, float* out, void* stream);
+                                   const float* positional_embedding, int n_state, void* out, unsigned flags, void* stream);
 
 /* The window cut of the decoding loop, transcribe.py:282-286 (and :150 with seek 0):
  *   mel_segment = pad_or_trim(mel[:, seek : seek + segment_size], N_FRAMES).to(device).to(dtype)

@@ -142,3 +142,20 @@ def test_fused_stem2_zero_padded_clips_lengths_and_pcm(b200):
     got = b200.log_mel_encoder_stem2(torch.from_numpy(pcm).to(DEV), *p)
     mel = b200.log_mel_spectrogram_batch(torch.from_numpy(pcm).to(DEV))
     assert torch.equal(got, b200.encoder_stem2(mel, *p))
+
+
+def test_stem2_half_output_is_the_rounded_float32_result(b200):
+    """`dtype=torch.float16` (model.py:197 `.to(x.dtype)` of a half-precision model): the float32 result rounded once."""
+    p = [t.to(DEV) for t in _params(384, 21)]
+    pos = _sinusoids(750, 384).to(DEV)
+    for n_frames in (1500, 1499, 37):
+        mel = (torch.rand(3, 80, n_frames, generator=torch.Generator().manual_seed(n_frames)) * 2.5 - 1.0).to(DEV)
+        e = pos[: (n_frames + 1) // 2] if n_frames != 1500 else pos
+        full = b200.encoder_stem2(mel, *p, e)
+        half = b200.encoder_stem2(mel, *p, e, dtype=torch.float16)
+        assert half.dtype == torch.float16 and half.shape == full.shape
+        assert torch.equal(half, full.half())
+    wave = torch.from_numpy(np.stack([signals.make_signal("gauss", 48000, 3), signals.make_signal("chirp", 48000, 4)])).to(DEV)
+    assert torch.equal(b200.log_mel_encoder_stem2(wave, *p, dtype=torch.float16), b200.log_mel_encoder_stem2(wave, *p).half())
+    with pytest.raises(ValueError):
+        b200.encoder_stem2(mel, *p, dtype=torch.bfloat16)

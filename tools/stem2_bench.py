@@ -40,15 +40,19 @@ def main():
 
     def conv2():
         _native.check(lib.b200mel_stem_conv2_gelu_device(h1.data_ptr(), clips, 3000, packed.data_ptr(), b2.data_ptr(), pos.data_ptr(),
-                                                         n_state, out.data_ptr(), s))
+                                                         n_state, out.data_ptr(), 0, s))
 
     def conv2_plain():
         _native.check(lib.b200mel_stem_conv2_gelu_device(h1.data_ptr(), clips, 3000, packed.data_ptr(), b2.data_ptr(), None,
-                                                         n_state, out.data_ptr(), s))
+                                                         n_state, out.data_ptr(), 0, s))
 
     t1 = timed(conv1, reps)
     t2 = timed(conv2, reps)
     t2_plain = timed(conv2_plain, reps)
+    out16 = torch.empty(clips, 1500, n_state, dtype=torch.float16, device=dev)
+    t2_half = timed(lambda: _native.check(lib.b200mel_stem_conv2_gelu_device(
+        h1.data_ptr(), clips, 3000, packed.data_ptr(), b2.data_ptr(), pos.data_ptr(), n_state, out16.data_ptr(), _native.FLAG_OUT_F16, s)), reps)
+    del out16
     t_stem = timed(lambda: b200.encoder_stem2(mel, w1, b1, packed, b2, pos), reps)
     t_all = timed(lambda: b200.log_mel_encoder_stem2(wave, w1, b1, packed, b2, pos), reps)
     flops2 = 2.0 * clips * 1500 * n_state * n_state * 3
@@ -57,6 +61,7 @@ def main():
     print(f"clips {clips} n_state {n_state}")
     print(f"conv1 + GELU -> half [B, 3000, {n_state}]   {t1:8.4f} ms  {bytes1 / t1 / 1e6:8.1f} GB/s")
     print(f"conv2 + GELU + pos -> [B, 1500, {n_state}]  {t2:8.4f} ms  {flops2 / t2 / 1e9:8.1f} TFLOP/s (f16 MMA)  {bytes2 / t2 / 1e6:8.1f} GB/s")
+    print(f"conv2 + GELU + pos -> half                {t2_half:8.4f} ms")
     print(f"conv2 + GELU without pos                  {t2_plain:8.4f} ms")
     print(f"encoder_stem2 (mel in)              {t_stem:8.4f} ms")
     print(f"log_mel_encoder_stem2 (waveform in) {t_all:8.4f} ms  = {clips * 30 / 3600 / (t_all * 1e-3):8.1f} audio-hours/s")
