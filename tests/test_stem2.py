@@ -159,3 +159,46 @@ def test_stem2_half_output_is_the_rounded_float32_result(b200):
     assert torch.equal(b200.log_mel_encoder_stem2(wave, *p, dtype=torch.float16), b200.log_mel_encoder_stem2(wave, *p).half())
     with pytest.raises(ValueError):
         b200.encoder_stem2(mel, *p, dtype=torch.bfloat16)
+
+
+@pytest.mark.parametrize("n_frames", [3000, 131, 514, 37])
+def test_stem2_kernels_write_inside_their_buffers(b200, n_frames):
+    """Both stem kernels through the C ABI into buffers with guard bands: nothing outside [batch, frames, n_state] is touched
+    (whole pieces leave by TMA tensor store, the partial ones at a clip's end by themselves; the padding frame of an odd
+    frame count is the caller's)."""
+    from asr_ttl_mtl_b200 import _native
+
+    lib = _native.load()
+    batch, n_state, guard = 3, 384, 4096
+    w1, b1, w2, b2 = [t.to(DEV) for t in _params(n_state, 31)]
+    packed = b200.pack_conv2_weight(w2)
+    mel = (torch.rand(batch, 80, n_frames, generator=torch.Generator().manual_seed(5)) * 2.5 - 1.0).to(DEV)
+    padded = n_frames + (n_frames & 1)
+    h_elems, o_elems = batch * padded * n_state, batch * (padded // 2) * n_state
+    h_buf = torch.full((guard + h_elems + guard,), 7.0, dtype=torch.float16, device=DEV)
+    o_buf = torch.full((guard + o_elems + guard,), 7.0, dtype=torch.float32, device=DEV)
+    h1 = h_buf[guard:guard + h_elems].view(batch, padded, n_state)
+    out = o_buf[guard:guard + o_elems].view(batch, padded // 2, n_state)
+    stream = torch.cuda.current_stream().cuda_stream
+    _native.check(lib.b200mel_stem_conv1_gelu_fm16_device(mel.data_ptr(), None, 0, batch, 80, n_frames, w1.data_ptr(), b1.data_ptr(),
+                                                          n_state, h1.data_ptr(), stream))
+    if padded != n_frames:
+        assert bool((h1[:, n_frames:] == 7.0).all())                       # the padding frame is not the kernel's to write
+        h1[:, n_frames:].zero_()
+    _native.check(lib.b200mel_stem_conv2_gelu_device(h1.data_ptr(), batch, padded, packed.data_ptr(), b2.data_ptr(), None, n_state,
+                                                     out.data_ptr(), 0, stream))
+    torch.cuda.synchronize()
+    for buf, n in ((h_buf, h_elems), (o_buf, o_elems)):
+        assert bool((buf[:guard] == 7.0).all()) and bool((buf[guard + n:] == 7.0).all())
+    assert torch.equal(out, b200.encoder_stem2(mel, w1, b1, packed, b2))
+    want = F.gelu(F.conv1d(mel, w1, b1, padding=1)).permute(0, 2, 1)
+    assert float((h1[:, :n_frames].float() - want).abs().max()) <= 5e-3    # conv1 in half, frames major
+    # bad arguments come back as status codes, not launches
+    assert lib.b200mel_stem_conv2_gelu_device(h1.data_ptr(), batch, padded + 1, packed.data_ptr(), b2.data_ptr(), None, n_state,
+                                              out.data_ptr(), 0, stream) != 0
+    assert lib.b200mel_stem_conv2_gelu_device(h1.data_ptr(), batch, padded, packed.data_ptr(), b2.data_ptr(), None, 100,
+                                              out.data_ptr(), 0, stream) != 0
+    assert lib.b200mel_stem_conv2_gelu_device(h1.data_ptr(), batch, padded, packed.data_ptr(), b2.data_ptr(), None, n_state,
+                                              out.data_ptr(), 1, stream) != 0
+    assert lib.b200mel_stem_conv2_gelu_device(None, batch, padded, packed.data_ptr(), b2.data_ptr(), None, n_state,
+                                              out.data_ptr(), 0, stream) != 0
