@@ -37,8 +37,9 @@ constexpr int kStemRows = kStemTile + 2;        // + one frame either side (kern
 constexpr int kStemN = 128;                     // channels per CTA = MMA M = TMEM lanes
 constexpr int kStemMels = 80;
 constexpr int kStemKChunks = kStemMels / 4;     // 16-byte K chunks (4 tf32)
-constexpr int kStemChunkBytes = kStemRows * 16; // 2080: one K chunk of the tile
-constexpr int kStemXBytes = kStemKChunks * kStemChunkBytes;          // 41600 per input buffer (a multiple of 128)
+constexpr int kStemChunkBytes = kStemRows * 16 + 16;   // 2096: one K chunk of the tile + 16 bytes, so that the loaders' 16-byte stores
+                                                       // (4 mel quads x 2 frame groups per quarter warp: chunk stride 524 words = 12 banks) hit 8 different bank groups
+constexpr int kStemXBytes = (kStemKChunks * kStemChunkBytes + 127) / 128 * 128;   // 41984 per input buffer (a multiple of 128)
 constexpr int kStemStages = 3;
 constexpr int kStemWarpMma = 8, kStemLoaderWarps = 8, kStemLoaderGroups = 1;   // warps 0-7 epilogue, 8 MMA issue, 9-16 loaders (one group of eight: a second group taking every other tile measured 2.5 % slower)
 constexpr int kStemWarps = kStemWarpMma + 1 + kStemLoaderGroups * kStemLoaderWarps, kStemThreads = kStemWarps * 32;
