@@ -140,9 +140,15 @@ class ClockSampler:
         self.max_mhz = None
         self._stop = threading.Event()
         self._thread = None
+        self._handle = None
+        self._nvml = None
         self.error = None
 
-    def __enter__(self):
+    def prepare(self):
+        """NVML start-up (tens of milliseconds): done BEFORE the barrier + synchronize in front of a timed region, so that the
+        GPU does not sit idle between the synchronize and the first timed launch."""
+        if self._handle is not None or self.error:
+            return self
         try:
             import pynvml
 
@@ -153,23 +159,31 @@ class ClockSampler:
                 ids = [v.strip() for v in visible.split(",") if v.strip()]
                 if self.index < len(ids) and ids[self.index].isdigit():
                     phys = int(ids[self.index])
-            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
-
-            def poll():
-                while not self._stop.is_set():
-                    try:
-                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
-                        self.reasons |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
-                    except Exception as e:  # keep the bench alive; report the gap
-                        self.error = repr(e)
-                        return
-                    time.sleep(0.002)
-
-            self._thread = threading.Thread(target=poll, daemon=True)
-            self._thread.start()
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
         except Exception as e:
             self.error = repr(e)
+        return self
+
+    def __enter__(self):
+        self.prepare()
+        if self._handle is None:
+            return self
+        pynvml, handle = self._nvml, self._handle
+
+        def poll():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                    self.reasons |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                except Exception as e:  # keep the bench alive; report the gap
+                    self.error = repr(e)
+                    return
+                time.sleep(0.002)
+
+        self._thread = threading.Thread(target=poll, daemon=True)
+        self._thread.start()
         return self
 
     def __exit__(self, *exc):
@@ -357,9 +371,10 @@ def workload_config(args, batch: int, where: str, world: int) -> dict:
 def timed_steps(step, steps: int, local_rank: int):
     """K steps between two events on the current stream, with clock sampling; returns (ms, clock summary)."""
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank).prepare()
     barrier()
     torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clocks:
+    with sampler as clocks:
         start.record()
         for i in range(steps):
             step(i)
